@@ -1,0 +1,67 @@
+// C-ABI of libcogaim_b200.so (declared in include/cogaim_b200.h).  No torch types, no exceptions.
+#include "../../include/cogaim_b200.h"
+
+#include "gemm.cuh"
+#include "host.h"
+
+namespace ca {
+const char* last_error_cstr();
+}
+
+extern "C" {
+
+const char* ca_last_error(void) { return ca::last_error_cstr(); }
+
+int ca_version(void) { return 1; }
+
+int ca_device_check(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    ca::set_error("no CUDA device visible: the Cognitive-Aim B200 path has no CPU fallback");
+    (void)cudaGetLastError();
+    return CA_STATUS_UNSUPPORTED;
+  }
+  if (device < 0 || device >= count) return ca::invalid("device index out of range");
+  int major = 0;
+  CA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) {
+    ca::set_error("device is not compute capability 10.x (sm_100a kernels only)");
+    return CA_STATUS_UNSUPPORTED;
+  }
+  return CA_STATUS_OK;
+}
+
+int ca_gemm_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K, int lda, int ldw, int batch,
+                 long long a_batch_stride, long long w_batch_stride, int epilogue, void* out, int ldo,
+                 long long out_batch_stride, const float* bias, const float* ls, const float* pos,
+                 int patches_per_img, float scale_log2, float* part_a, float* part_b, const float* col_max,
+                 const float* col_rinv, void* stream) {
+  ca::GemmArgs a;
+  a.A = reinterpret_cast<const __nv_bfloat16*>(A);
+  a.W = reinterpret_cast<const __nv_bfloat16*>(W);
+  a.M = M;
+  a.N = N;
+  a.K = K;
+  a.lda = lda;
+  a.ldw = ldw;
+  a.batch = batch;
+  a.a_batch_stride = a_batch_stride;
+  a.w_batch_stride = w_batch_stride;
+  a.epilogue = epilogue;
+  a.out = out;
+  a.ldo = ldo;
+  a.out_batch_stride = out_batch_stride;
+  a.bias = bias;
+  a.ls = ls;
+  a.pos = pos;
+  a.patches_per_img = patches_per_img;
+  a.scale_log2 = scale_log2;
+  a.part_a = part_a;
+  a.part_b = part_b;
+  a.col_max = col_max;
+  a.col_rinv = col_rinv;
+  return ca::gemm_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,418 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C = epilogue(A * W^T), bf16 operands, fp32
+// accumulation in TMEM.
+//
+//   warp 0      : TMA producer   (one lane) — A/W tiles -> 128B-swizzled smem ring, mbarrier complete_tx
+//   warp 1      : MMA issuer     (one lane) — tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction,
+//                                  tcgen05.commit releases smem stages and publishes accumulators;
+//                                  the whole warp allocates / frees TMEM
+//   warps 2..9  : epilogue       — tcgen05.ld from the warp's TMEM lane quadrant (warp_id % 4), two warps per
+//                                  quadrant split the BN columns; fused bias / GELU / LayerScale+residual /
+//                                  pos-embed / softmax-statistics epilogues straight to global memory
+//
+// Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// Tiles are scheduled statically (tile = blockIdx.x + i * gridDim.x) with the N index fastest so the CTAs
+// working at the same time share A tiles through L2.
+//
+// Replaces the ATen/cuBLAS call sites listed in SURVEY.md §2.1 (HF modeling_dinov2.py:148,199-201,246,324-328;
+// reference src/model.py:192-197).
+#include "common.cuh"
+#include "gemm.cuh"
+#include "host.h"
+
+namespace ca {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // one 128-byte swizzle atom of bf16
+constexpr int kNumEpiWarps = 8;
+constexpr int kGemmThreads = (2 + kNumEpiWarps) * 32;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;  // 512 or 256: power of two
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmKernelArgs {
+  int M, N, K;
+  int m_tiles, n_tiles, total_tiles;
+  int w_batched;
+  void* out;
+  int ldo;
+  long long out_batch_stride;
+  const float* bias;
+  const float* ls;
+  const float* pos;
+  int patches_per_img;
+  float scale_log2;
+  float* part_a;
+  float* part_b;
+  const float* col_max;
+  const float* col_rinv;
+  int partials;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// One epilogue warp: rows [32*q, 32*q+32) of the tile (q = warp_id % 4), columns [col0, col0 + BN/2).
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, uint32_t tmem_acc, int b, int mt, int nt,
+                                              int quad, int half) {
+  constexpr int kSpan = BN / 2;
+  const int lane = lane_id();
+  const int row = mt * BM + quad * 32 + lane;           // row inside batch b
+  const int col_base = nt * BN + half * kSpan;          // first column this warp owns
+  const bool row_ok = row < p.M;
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(half * kSpan);
+
+  if constexpr (EPI == EPI_ROWSTATS) {
+    // pass 1: max ; pass 2: sum exp2(s - max).  TMEM re-read is cheaper than holding kSpan registers.
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kSpan; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float s = __uint_as_float(v[j]) * p.scale_log2;
+        if (col_base + c + j < p.N) mx = fmaxf(mx, s);
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kSpan; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float s = __uint_as_float(v[j]) * p.scale_log2;
+        if (col_base + c + j < p.N) sum += fast_exp2(s - mx);
+      }
+    }
+    if (row_ok) {
+      const size_t o = (static_cast<size_t>(b) * p.M + row) * p.partials + nt * 2 + half;
+      p.part_a[o] = mx;
+      p.part_b[o] = sum;
+    }
+    return;
+  } else if constexpr (EPI == EPI_COLSUM) {
+    const float* cmax = p.col_max + static_cast<size_t>(b) * p.N;
+    const float* cinv = p.col_rinv + static_cast<size_t>(b) * p.N;
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kSpan; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = col_base + c + j;
+        if (col < p.N) {
+          const float s = __uint_as_float(v[j]) * p.scale_log2;
+          sum += fast_exp2(s - __ldg(cmax + col)) * __ldg(cinv + col);
+        }
+      }
+    }
+    if (row_ok) {
+      const size_t o = (static_cast<size_t>(b) * p.M + row) * p.partials + nt * 2 + half;
+      p.part_a[o] = sum;
+    }
+    return;
+  } else {
+    // Dense epilogues: 32 columns at a time, one row per thread.
+    size_t orow;
+    if constexpr (EPI == EPI_PATCH_F32) {
+      const int img = row / p.patches_per_img;
+      const int pidx = row - img * p.patches_per_img;
+      orow = static_cast<size_t>(img) * (p.patches_per_img + 1) + 1 + pidx;
+    } else {
+      orow = static_cast<size_t>(row);
+    }
+#pragma unroll 1
+    for (int c = 0; c < kSpan; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + c, v);
+      tmem_ld_wait();
+      const int col = col_base + c;
+      // N is a multiple of 32 for the dense epilogues (checked on the host), so `col < N` is warp-uniform;
+      // `row_ok` is per lane, hence no `continue` here: the next tcgen05.ld needs a converged warp.
+      if (row_ok && col < p.N) {
+      float acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+      if constexpr (EPI != EPI_F32) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(b4 + j);
+          acc[4 * j + 0] += t.x;
+          acc[4 * j + 1] += t.y;
+          acc[4 * j + 2] += t.z;
+          acc[4 * j + 3] += t.w;
+        }
+      }
+      if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16) {
+        if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+        }
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride +
+                           orow * p.ldo + col;
+        uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 t;
+          t.x = pack_bf16x2(acc[8 * j + 0], acc[8 * j + 1]);
+          t.y = pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]);
+          t.z = pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]);
+          t.w = pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]);
+          o4[j] = t;
+        }
+      } else {
+        float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride + orow * p.ldo + col;
+        float4* o4 = reinterpret_cast<float4*>(o);
+        if constexpr (EPI == EPI_RESID_F32) {
+          const float4* l4 = reinterpret_cast<const float4*>(p.ls + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 l = __ldg(l4 + j);
+            float4 x = o4[j];
+            x.x = fmaf(l.x, acc[4 * j + 0], x.x);
+            x.y = fmaf(l.y, acc[4 * j + 1], x.y);
+            x.z = fmaf(l.z, acc[4 * j + 2], x.z);
+            x.w = fmaf(l.w, acc[4 * j + 3], x.w);
+            o4[j] = x;
+          }
+        } else if constexpr (EPI == EPI_PATCH_F32) {
+          const int pidx = row % p.patches_per_img;
+          const float4* q4 = reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + pidx) * p.N + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 q = __ldg(q4 + j);
+            o4[j] = make_float4(acc[4 * j + 0] + q.x, acc[4 * j + 1] + q.y, acc[4 * j + 2] + q.z, acc[4 * j + 3] + q.w);
+          }
+        } else {  // EPI_F32
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o4[j] = make_float4(acc[4 * j + 0], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
+      }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const GemmKernelArgs p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms are 1024 B; align the ring explicitly (dynamic smem is only 16 B aligned by contract).
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                        // [kStages] TMA -> MMA
+  uint64_t* empty_bar = bars + Cfg::kStages;        // [kStages] MMA -> TMA
+  uint64_t* acc_full = bars + 2 * Cfg::kStages;     // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;               // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = warp_id();
+  const int lane = lane_id();
+  const int kblocks = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], kNumEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int rest = tile / p.n_tiles;
+        const int mt = rest % p.m_tiles;
+        const int b = rest / p.m_tiles;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_3d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK, mt * BM, b);
+          tma_load_3d(smem_b + stage * Cfg::kBBytes, &tmap_w, &full_bar[stage], kb * BK, nt * BN,
+                      p.w_batched ? b : 0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes per 16-element K step inside the swizzle atom  (descriptor address unit = 16 B)
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&acc_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    const int e = warp - 2;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int half = e >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      const int rest = tile / p.n_tiles;
+      const int mt = rest % p.m_tiles;
+      const int b = rest / p.m_tiles;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<BN, EPI>(p, tmem_base + static_cast<uint32_t>(acc * BN), b, mt, nt, quad, half);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int EPI>
+int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmKernelArgs& ka, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  int grid = ka.total_tiles < sm_count() ? ka.total_tiles : sm_count();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, ka);
+  CA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
+  CA_REQUIRE(a.A && a.W, "gemm: null operand");
+  CA_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && a.batch > 0, "gemm: non-positive dimension");
+  CA_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 elements (16 B) for TMA");
+  CA_REQUIRE(a.K <= a.lda && a.K <= a.ldw, "gemm: K exceeds a leading dimension");
+  const bool stats = (a.epilogue == EPI_ROWSTATS || a.epilogue == EPI_COLSUM);
+  const int bn = stats ? 128 : 256;
+  if (!stats) {
+    CA_REQUIRE(a.N % 32 == 0, "gemm: N must be a multiple of 32 for the dense epilogues");
+    CA_REQUIRE(a.out != nullptr, "gemm: null output");
+    CA_REQUIRE(a.epilogue == EPI_F32 || a.bias != nullptr, "gemm: null bias");
+    const int vec = (a.epilogue == EPI_BIAS_BF16 || a.epilogue == EPI_GELU_BF16) ? 8 : 4;
+    CA_REQUIRE(a.ldo % vec == 0, "gemm: ldo must keep rows 16-byte aligned");
+    CA_REQUIRE(a.epilogue != EPI_RESID_F32 || a.ls != nullptr, "gemm: null LayerScale");
+    CA_REQUIRE(a.epilogue != EPI_PATCH_F32 || (a.pos != nullptr && a.patches_per_img > 0), "gemm: null pos-embed");
+  } else {
+    CA_REQUIRE(a.part_a != nullptr, "gemm: null partial buffer");
+    CA_REQUIRE(a.epilogue != EPI_ROWSTATS || a.part_b != nullptr, "gemm: null partial-sum buffer");
+    CA_REQUIRE(a.epilogue != EPI_COLSUM || (a.col_max && a.col_rinv), "gemm: null column statistics");
+  }
+
+  CUtensorMap ta, tw;
+  const long long abs = a.batch > 1 ? a.a_batch_stride : static_cast<long long>(a.M) * a.lda;
+  CA_REQUIRE(abs % 8 == 0, "gemm: A batch stride must be a multiple of 8 elements");
+  CA_TRY(make_tmap_3d(&ta, a.A, a.batch, a.M, a.K, a.lda, abs, BM));
+  const bool wb = a.batch > 1 && a.w_batch_stride != 0;
+  const long long wbs = wb ? a.w_batch_stride : static_cast<long long>(a.N) * a.ldw;
+  CA_REQUIRE(wbs % 8 == 0, "gemm: W batch stride must be a multiple of 8 elements");
+  CA_TRY(make_tmap_3d(&tw, a.W, wb ? a.batch : 1, a.N, a.K, a.ldw, wbs, bn));
+
+  GemmKernelArgs ka;
+  ka.M = a.M;
+  ka.N = a.N;
+  ka.K = a.K;
+  ka.m_tiles = (a.M + BM - 1) / BM;
+  ka.n_tiles = (a.N + bn - 1) / bn;
+  ka.total_tiles = ka.m_tiles * ka.n_tiles * a.batch;
+  ka.w_batched = wb ? 1 : 0;
+  ka.out = a.out;
+  ka.ldo = a.ldo;
+  ka.out_batch_stride = a.out_batch_stride;
+  ka.bias = a.bias;
+  ka.ls = a.ls;
+  ka.pos = a.pos;
+  ka.patches_per_img = a.patches_per_img;
+  ka.scale_log2 = a.scale_log2;
+  ka.part_a = a.part_a;
+  ka.part_b = a.part_b;
+  ka.col_max = a.col_max;
+  ka.col_rinv = a.col_rinv;
+  ka.partials = gemm_stats_partials(a.N);
+
+  switch (a.epilogue) {
+    case EPI_BIAS_BF16: return launch_inst<256, EPI_BIAS_BF16>(ta, tw, ka, stream);
+    case EPI_GELU_BF16: return launch_inst<256, EPI_GELU_BF16>(ta, tw, ka, stream);
+    case EPI_RESID_F32: return launch_inst<256, EPI_RESID_F32>(ta, tw, ka, stream);
+    case EPI_PATCH_F32: return launch_inst<256, EPI_PATCH_F32>(ta, tw, ka, stream);
+    case EPI_F32: return launch_inst<256, EPI_F32>(ta, tw, ka, stream);
+    case EPI_ROWSTATS: return launch_inst<128, EPI_ROWSTATS>(ta, tw, ka, stream);
+    case EPI_COLSUM: return launch_inst<128, EPI_COLSUM>(ta, tw, ka, stream);
+    default: return invalid("gemm: unknown epilogue");
+  }
+}
+
+}  // namespace ca

@@ -1,0 +1,46 @@
+// Host-side plumbing shared by the launchers: error capture and TMA tensor-map encoding.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace ca {
+
+void set_error(const std::string& msg);  // records the message returned by ca_last_error()
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+int invalid(const char* what);
+
+#define CA_CUDA(call)                                                        \
+  do {                                                                       \
+    cudaError_t _e = (call);                                                 \
+    if (_e != cudaSuccess) return ca::cuda_fail(_e, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define CA_REQUIRE(cond, msg)              \
+  do {                                     \
+    if (!(cond)) return ca::invalid(msg);  \
+  } while (0)
+
+#define CA_TRY(expr)            \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != 0) return _s;     \
+  } while (0)
+
+// bf16 tensor map, 128B swizzle, inner box = 64 elements (128 bytes).
+// dims/strides are given innermost-first; strides in BYTES for dims 1..rank-1.
+int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box);
+
+// Convenience: row-major [rows, cols] bf16 matrix with leading dimension ld (elements),
+// optionally batched (batch stride in elements); box = [box_rows, 64].
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint64_t batch_stride, uint32_t box_rows);
+
+int sm_count();
+
+}  // namespace ca

@@ -1,0 +1,102 @@
+"""tcgen05 GEMM (csrc/gemm.cu) against torch fp32 matmul of the same bf16-rounded operands."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, dev, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev)
+
+
+def _relerr(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 768), (300, 768, 768), (1370 * 2, 2304, 768),
+                                   (1000, 768, 3072), (2738, 768, 592)])
+def test_gemm_f32(cuda_device, M, N, K):
+    from cognitive_aim_depth_estimation_b200 import ops
+    A = _rand((M, K), cuda_device, 1).bfloat16()
+    W = _rand((N, K), cuda_device, 2, 0.05).bfloat16()
+    out = torch.full((M, N), float("nan"), device=cuda_device)
+    ops.gemm(A, W, ops.EPI_F32, out)
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t()
+    assert torch.isfinite(out).all()
+    assert _relerr(out, ref) < 2e-5, _relerr(out, ref)
+
+
+def test_gemm_bias_bf16_and_gelu(cuda_device):
+    from cognitive_aim_depth_estimation_b200 import ops
+    M, N, K = 1370, 3072, 768
+    A = _rand((M, K), cuda_device, 3).bfloat16()
+    W = _rand((N, K), cuda_device, 4, 0.04).bfloat16()
+    bias = _rand((N,), cuda_device, 5, 0.1)
+    ref = A.float() @ W.float().t() + bias
+    out = torch.zeros((M, N), device=cuda_device, dtype=torch.bfloat16)
+    ops.gemm(A, W, ops.EPI_BIAS_BF16, out, bias=bias)
+    assert _relerr(out, ref) < 4e-3
+    ops.gemm(A, W, ops.EPI_GELU_BF16, out, bias=bias)
+    assert _relerr(out, torch.nn.functional.gelu(ref)) < 4e-3
+
+
+def test_gemm_resid_inplace(cuda_device):
+    from cognitive_aim_depth_estimation_b200 import ops
+    M, N, K = 1370 * 3, 768, 3072
+    A = _rand((M, K), cuda_device, 6).bfloat16()
+    W = _rand((N, K), cuda_device, 7, 0.02).bfloat16()
+    bias = _rand((N,), cuda_device, 8, 0.1)
+    ls = _rand((N,), cuda_device, 9, 1.0)
+    x = _rand((M, N), cuda_device, 10)
+    ref = x + ls * (A.float() @ W.float().t() + bias)
+    ops.gemm(A, W, ops.EPI_RESID_F32, x, bias=bias, ls=ls)
+    assert _relerr(x, ref) < 1e-5
+
+
+def test_gemm_patch_embed(cuda_device):
+    from cognitive_aim_depth_estimation_b200 import ops
+    B, Np, D, K = 3, 256, 768, 592
+    A = _rand((B * Np, K), cuda_device, 11).bfloat16()
+    A[:, 588:] = 0
+    W = _rand((D, K), cuda_device, 12, 0.05).bfloat16()
+    bias = _rand((D,), cuda_device, 13, 0.1)
+    pos = _rand((Np + 1, D), cuda_device, 14, 0.02)
+    x = torch.zeros((B, Np + 1, D), device=cuda_device)
+    ops.gemm(A, W, ops.EPI_PATCH_F32, x.view(-1, D), bias=bias, pos=pos, patches_per_img=Np)
+    ref = (A.float() @ W.float().t() + bias).view(B, Np, D) + pos[1:]
+    assert _relerr(x[:, 1:], ref) < 1e-5
+    assert (x[:, 0] == 0).all()
+
+
+@pytest.mark.parametrize("N,D", [(256, 768), (1369, 768)])
+def test_gemm_focal_stats(cuda_device, N, D):
+    """Row statistics (pass A) and softmax column sums (pass B) == column-mean of a row softmax."""
+    from cognitive_aim_depth_estimation_b200 import ops
+    B = 2
+    q = _rand((B, N, D), cuda_device, 15).bfloat16()
+    k = _rand((B, N, D), cuda_device, 16, 0.5).bfloat16()
+    scale = 1.0 / math.sqrt(96.0)
+    P = ops.stats_partials(N)
+    pm = torch.zeros((B, N, P), device=cuda_device)
+    ps = torch.zeros((B, N, P), device=cuda_device)
+    ops.gemm(q, k, ops.EPI_ROWSTATS, None, M=N, N=N, K=D, lda=D, ldw=D, batch=B, a_batch_stride=N * D,
+             w_batch_stride=N * D, scale_log2=scale * ops.LOG2E, part_a=pm, part_b=ps)
+    s = torch.einsum("bid,bjd->bij", q.float(), k.float()) * scale
+    s2 = s * ops.LOG2E
+    rmax = pm.max(dim=-1).values
+    assert torch.allclose(rmax, s2.max(dim=-1).values, rtol=1e-5, atol=1e-4)
+    rsum = (ps * torch.exp2(pm - rmax[..., None])).sum(-1)
+    ref_sum = torch.exp2(s2 - s2.max(dim=-1, keepdim=True).values).sum(-1)
+    assert torch.allclose(rsum, ref_sum, rtol=2e-3)
+    # pass B: A = keys, W = queries  ->  acc[j, i] = s[i, j]
+    pc = torch.zeros((B, N, P), device=cuda_device)
+    rinv = (1.0 / rsum).contiguous()
+    ops.gemm(k, q, ops.EPI_COLSUM, None, M=N, N=N, K=D, lda=D, ldw=D, batch=B, a_batch_stride=N * D,
+             w_batch_stride=N * D, scale_log2=scale * ops.LOG2E, part_a=pc, col_max=rmax.contiguous(), col_rinv=rinv)
+    colmean = pc.sum(-1) / N
+    ref = torch.softmax(s, dim=-1).mean(dim=1)
+    assert torch.allclose(colmean, ref, rtol=5e-3, atol=1e-7), (colmean - ref).abs().max()
