@@ -1,7 +1,9 @@
 // C-ABI of libcogaim_b200.so (declared in include/cogaim_b200.h).  No torch types, no exceptions.
 #include "../../include/cogaim_b200.h"
 
+#include "attention.cuh"
 #include "gemm.cuh"
+#include "rowops.cuh"
 #include "host.h"
 
 namespace ca {
@@ -62,6 +64,37 @@ int ca_gemm_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K, int 
   a.col_max = col_max;
   a.col_rinv = col_rinv;
   return ca::gemm_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+int ca_attention_bf16(const uint16_t* qkv, uint16_t* out, int B, int T, int H, void* stream) {
+  return ca::attention_launch(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), B, T,
+                              H, static_cast<cudaStream_t>(stream));
+}
+
+int ca_patchify_f32(const float* images, uint16_t* patches, int B, int S, void* stream) {
+  return ca::patchify_f32_launch(images, reinterpret_cast<__nv_bfloat16*>(patches), B, S,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int ca_preprocess_u8(const uint8_t* images, uint16_t* patches, int B, int S, const float* h_mean3,
+                     const float* h_std3, void* stream) {
+  return ca::preprocess_u8_launch(images, reinterpret_cast<__nv_bfloat16*>(patches), B, S, h_mean3, h_std3,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int ca_cls_rows(float* x, const float* cls, const float* pos, int B, int T, int D, void* stream) {
+  return ca::cls_rows_launch(x, cls, pos, B, T, D, static_cast<cudaStream_t>(stream));
+}
+
+int ca_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_is_bf16, int rows, int D,
+                 float eps, void* stream) {
+  return ca::layernorm_launch(x, gamma, beta, out, out_is_bf16, rows, D, eps, static_cast<cudaStream_t>(stream));
+}
+
+int ca_focal_input(const float* tokens, const float* pe, const float* rowscale, uint16_t* xin, int B, int N, int D,
+                   void* stream) {
+  return ca::focal_input_launch(tokens, pe, rowscale, reinterpret_cast<__nv_bfloat16*>(xin), B, N, D,
+                                static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

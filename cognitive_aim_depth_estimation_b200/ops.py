@@ -59,3 +59,52 @@ def gemm(A, W, epilogue, out=None, *, M=None, N=None, K=None, lda=None, ldw=None
 
 
 LOG2E = math.log2(math.e)
+
+PATCH_ROW_STRIDE = 592
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def attention(qkv, out, B, T, H):
+    """out[B*T, H*64] = softmax(QK^T/8)V per (image, head) (csrc/attention.cu)."""
+    _req(qkv, torch.bfloat16, "qkv")
+    _req(out, torch.bfloat16, "out")
+    check(_lib.load().ca_attention_bf16(ptr(qkv), ptr(out), B, T, H, stream_ptr()), "ca_attention_bf16")
+    return out
+
+
+def patchify_f32(images, patches):
+    _req(images, torch.float32, "images")
+    _req(patches, torch.bfloat16, "patches")
+    B, _, S, _ = images.shape
+    check(_lib.load().ca_patchify_f32(ptr(images), ptr(patches), B, S, stream_ptr()), "ca_patchify_f32")
+    return patches
+
+
+def preprocess_u8(images_hwc, patches, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    import ctypes as C
+    _req(images_hwc, torch.uint8, "images")
+    _req(patches, torch.bfloat16, "patches")
+    B, S = images_hwc.shape[0], images_hwc.shape[1]
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    check(_lib.load().ca_preprocess_u8(ptr(images_hwc), ptr(patches), B, S, m, s, stream_ptr()), "ca_preprocess_u8")
+    return patches
+
+
+def cls_rows(x, cls, pos, B, T, D):
+    check(_lib.load().ca_cls_rows(ptr(x), ptr(cls), ptr(pos), B, T, D, stream_ptr()), "ca_cls_rows")
+
+
+def layernorm(x, gamma, beta, out, eps=1e-6):
+    _req(x, torch.float32, "x")
+    rows, D = x.numel() // x.shape[-1], x.shape[-1]
+    check(_lib.load().ca_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), int(out.dtype == torch.bfloat16), rows, D,
+                                   eps, stream_ptr()), "ca_layernorm")
+    return out
+
+
+def focal_input(tokens, pe, rowscale, xin, B, N, D):
+    check(_lib.load().ca_focal_input(ptr(tokens), ptr(pe), ptr(rowscale), ptr(xin), B, N, D, stream_ptr()),
+          "ca_focal_input")
+    return xin

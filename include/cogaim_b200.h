@@ -58,6 +58,29 @@ int ca_gemm_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K, int 
                  int patches_per_img, float scale_log2, float* part_a, float* part_b, const float* col_max,
                  const float* col_rinv, void* stream);
 
+/* Backbone attention --------------------------------------------------------------------------- */
+/* out[B*T, H*64] = softmax(Q K^T / 8) V per (image, head); qkv is the fused [B*T, 3*H*64] activation
+ * (Q | K | V column blocks).  Replaces F.scaled_dot_product_attention at HF modeling_dinov2.py:215-229. */
+int ca_attention_bf16(const uint16_t* qkv, uint16_t* out, int B, int T, int H, void* stream);
+
+/* Bandwidth-bound row kernels ------------------------------------------------------------------- */
+/* fp32 CHW images [B,3,S,S] (the tensor `forward` receives) -> bf16 patch rows [B*(S/14)^2, 592]
+ * (column k = c*196 + ky*14 + kx, columns 588..591 zero).  HF modeling_dinov2.py:139-148 (im2col of the conv). */
+int ca_patchify_f32(const float* images, uint16_t* patches, int B, int S, void* stream);
+/* uint8 HWC images [B,S,S,3] -> /255 -> (x-mean)/std -> bf16 patch rows.  demo.py:162-166 (ToTensor + Normalize;
+ * the source is already S x S so Resize is the identity).  h_mean3 / h_std3 are HOST pointers to 3 floats. */
+int ca_preprocess_u8(const uint8_t* images, uint16_t* patches, int B, int S, const float* h_mean3,
+                     const float* h_std3, void* stream);
+/* x[b, 0, :] = cls + pos[0]  (HF modeling_dinov2.py:108-112). x is the fp32 residual stream [B, T, D]. */
+int ca_cls_rows(float* x, const float* cls, const float* pos, int B, int T, int D, void* stream);
+/* LayerNorm(D=768) of fp32 rows -> bf16 (out_is_bf16=1) or fp32.  HF modeling_dinov2.py:354,359,449. */
+int ca_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_is_bf16, int rows, int D,
+                 float eps, void* stream);
+/* xin[b,n,:] = bf16(tokens[b,1+n,:] * rowscale[b,n] + pe[n,:]); rowscale may be NULL (=1).
+ * reference src/model.py:184 (PE add) and :426 (re-focus, folded into a per-row scale). */
+int ca_focal_input(const float* tokens, const float* pe, const float* rowscale, uint16_t* xin, int B, int N, int D,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

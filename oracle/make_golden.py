@@ -1,0 +1,144 @@
+"""Generate tests/golden/* by running the UNMODIFIED reference (/root/reference) on CPU fp32.
+
+Runs only in the build container (the reference does not travel to the GPU box).  The only patch is the
+network access at reference src/model.py:814 (`Dinov2Model.from_pretrained`) -> random-init
+`Dinov2Model(Dinov2Config(image_size=518, patch_size=14))`.  Seed protocol: weights
+`torch.manual_seed(0)`; images seed 1234; EXIF seed 1236; `torch.manual_seed(11)` before every call.
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz / *.json
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+from oracle import cogaim_oracle as orc  # noqa: E402  (inputs + digest helper only)
+
+WEIGHT_SEED, CALL_SEED = 0, 11
+
+
+def load_reference():
+    from transformers import Dinov2Config, Dinov2Model
+    Dinov2Model.from_pretrained = staticmethod(
+        lambda name, *a, **k: Dinov2Model(Dinov2Config(image_size=518, patch_size=14)))
+    sys.path.insert(0, REF)
+    import src.model as ref  # noqa
+    return ref
+
+
+def make_model(ref, cfg_path):
+    cfg = yaml.safe_load(open(cfg_path))
+    cfg.setdefault("cognitive_modules", ["ambient_stream", "iterative_focal_stream", "exif_prior_database"])  # demo.py:46-52
+    torch.manual_seed(WEIGHT_SEED)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = ref.create_model(cfg, {"num_cameras": 71}).eval()
+    return model
+
+
+def effective_attrs(model):
+    fs = model.focal_stream
+    return {
+        "use_lora": bool(model.use_lora), "use_ambient": bool(model.use_ambient), "use_focal": bool(model.use_focal),
+        "use_exif": bool(model.use_exif), "use_iterative": bool(model.use_iterative),
+        "feature_dim": int(model.feature_dim), "fusion_dim": int(model.fusion_dim),
+        "num_iterations": int(fs.num_iterations), "focus_strength": float(fs.focus_strength),
+        "curiosity_guided": bool(fs.curiosity_guided),
+        "n_state_tensors": len(model.state_dict()),
+        "n_params": int(sum(p.numel() for p in model.parameters())),
+    }
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = load_reference()
+    torch.set_num_threads(os.cpu_count())
+
+    # 1. effective config of every shipped YAML (quirk 1) ------------------------------------------------
+    attrs = {}
+    cfgs = [os.path.join(REF, "configs", "experiment_B.yaml")] + sorted(
+        os.path.join(REF, "eval_configs", f) for f in os.listdir(os.path.join(REF, "eval_configs")))
+    model = None
+    for c in cfgs:
+        m = make_model(ref, c)
+        attrs[os.path.relpath(c, REF)] = effective_attrs(m)
+        if model is None:
+            model = m
+    json.dump(attrs, open(os.path.join(OUT, "effective_config.json"), "w"), indent=1, sort_keys=True)
+
+    # 2. weights digest ----------------------------------------------------------------------------------
+    sd = model.state_dict()
+    dig = orc.state_dict_digest(sd)
+    json.dump({"seed": WEIGHT_SEED, "names": list(sd.keys()), "shapes": {k: list(v.shape) for k, v in sd.items()},
+               "digest": dig}, open(os.path.join(OUT, "state_dict_seed0.json"), "w"))
+
+    # 3. guided forward, all 9 instructions ----------------------------------------------------------------
+    def guided(S, B, instr, call_seed=CALL_SEED):
+        x = orc.synthetic_images(B, S)
+        ex = orc.synthetic_exif(B)
+        if hasattr(model, "_last_attention_weights"):
+            delattr(model, "_last_attention_weights")  # demo.py:334-335
+        torch.manual_seed(call_seed)
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            d, c, h = model.forward_with_guidance(x, ex, instr, return_attention=True)
+        return d.numpy(), c.numpy(), h.numpy()
+
+    out = {}
+    for S, B in ((224, 2), (518, 1)):
+        for ins in orc.INSTRUCTIONS:
+            d, c, h = guided(S, B, ins)
+            key = f"S{S}_B{B}_{ins}"
+            out[key + "_depth"], out[key + "_conf"], out[key + "_heat"] = d, c, h
+            print(key, d.ravel(), c.ravel(), h.argmax(-1))
+    # alias / case / unknown-string / tensor-guidance semantics at S=224
+    for ins in ("TopLeft", "CENTER", "nonsense"):
+        d, c, h = guided(224, 2, ins)
+        key = f"S224_B2_{ins}"
+        out[key + "_depth"], out[key + "_conf"], out[key + "_heat"] = d, c, h
+    gvec = torch.linspace(0.5, 4.0, 196)  # 14x14 guidance on a 16x16 grid -> bilinear resize (:1386-1398)
+    d, c, h = guided(224, 2, gvec)
+    out["S224_B2_tensor196_depth"], out["S224_B2_tensor196_conf"], out["S224_B2_tensor196_heat"] = d, c, h
+    np.savez_compressed(os.path.join(OUT, "guided.npz"), **out)
+
+    # 4. un-guided forward (with and without EXIF) -----------------------------------------------------------
+    out = {}
+    for S, B in ((224, 2),):
+        x = orc.synthetic_images(B, S)
+        for tag, ex in (("exif", orc.synthetic_exif(B)), ("noexif", None)):
+            if hasattr(model, "_last_attention_weights"):
+                delattr(model, "_last_attention_weights")
+            torch.manual_seed(CALL_SEED)
+            with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+                d, c, h = model(x, ex, return_attention=True)
+            key = f"S{S}_B{B}_{tag}"
+            out[key + "_depth"], out[key + "_conf"], out[key + "_heat"] = d.numpy(), c.numpy(), h.numpy()
+            out[key + "_fusion"] = model.fusion_features.numpy()
+            print(key, d.ravel(), c.ravel())
+    np.savez_compressed(os.path.join(OUT, "unguided.npz"), **out)
+
+    # 5. backbone tokens (HF Dinov2Model inside the reference model) ------------------------------------------
+    out = {}
+    for S, B in ((224, 2), (518, 1)):
+        x = orc.synthetic_images(B, S)
+        with torch.no_grad():
+            t = model.backbone(x, output_hidden_states=True).last_hidden_state
+        out[f"S{S}_B{B}_tokens_head"] = t[:, :8, :32].numpy()
+        out[f"S{S}_B{B}_tokens_tail"] = t[:, -4:, -32:].numpy()
+        out[f"S{S}_B{B}_token_norms"] = t.norm(dim=-1).numpy()
+    np.savez_compressed(os.path.join(OUT, "backbone.npz"), **out)
+    print("golden vectors written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

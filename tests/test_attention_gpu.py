@@ -1,0 +1,27 @@
+"""tcgen05 flash attention (csrc/attention.cu) against torch fp32 softmax attention on the same bf16 inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(qkv, B, T, H):
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)  # [3][B,H,T,64]
+    att = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v
+    return att.transpose(1, 2).reshape(B * T, H * 64)
+
+
+@pytest.mark.parametrize("B,T,H,scale", [(1, 128, 1, 1.0), (1, 257, 2, 1.0), (2, 1370, 12, 1.0), (1, 1370, 12, 4.0),
+                                         (1, 100, 3, 2.0)])
+def test_attention_matches_fp32(cuda_device, B, T, H, scale):
+    from cognitive_aim_depth_estimation_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    qkv = (torch.randn(B * T, 3 * H * 64, generator=g) * scale).to(cuda_device).bfloat16()
+    out = torch.full((B * T, H * 64), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, T, H)
+    torch.cuda.synchronize()
+    ref = _ref(qkv, B, T, H)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    assert rel < 8e-3, (rel, err)

@@ -1,0 +1,90 @@
+"""Bandwidth-bound row kernels (csrc/rowops.cu) against their torch fp32 definitions."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _unfold_ref(images):
+    """[B,3,S,S] -> [B*g*g, 588] with column k = c*196 + ky*14 + kx (Conv2d weight.flatten(1) order)."""
+    B, C, S, _ = images.shape
+    g = S // 14
+    x = images[:, :, :g * 14, :g * 14].reshape(B, C, g, 14, g, 14).permute(0, 2, 4, 1, 3, 5)
+    return x.reshape(B * g * g, C * 196)
+
+
+@pytest.mark.parametrize("B,S", [(2, 224), (1, 518), (3, 70)])
+def test_patchify_f32(cuda_device, B, S):
+    from cognitive_aim_depth_estimation_b200 import ops
+    img = torch.randn(B, 3, S, S, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    g = S // 14
+    patches = torch.full((B * g * g, ops.PATCH_ROW_STRIDE), 7.0, device=cuda_device, dtype=torch.bfloat16)
+    ops.patchify_f32(img, patches)
+    assert torch.equal(patches[:, :588], _unfold_ref(img).bfloat16())
+    assert (patches[:, 588:] == 0).all()
+
+
+def test_patchify_equals_conv(cuda_device):
+    """patch rows x flattened conv weight == the reference's Conv2d(3,768,14,14) (HF modeling_dinov2.py:139-148)."""
+    from cognitive_aim_depth_estimation_b200 import ops
+    img = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(2)).to(cuda_device)
+    w = torch.randn(768, 3, 14, 14, generator=torch.Generator().manual_seed(3)).to(cuda_device) * 0.02
+    patches = torch.zeros((2 * 256, ops.PATCH_ROW_STRIDE), device=cuda_device, dtype=torch.bfloat16)
+    ops.patchify_f32(img, patches)
+    got = patches[:, :588].float() @ w.flatten(1).t()
+    ref = F.conv2d(img.bfloat16().float(), w, stride=14).flatten(2).transpose(1, 2).reshape(-1, 768)
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_preprocess_u8(cuda_device):
+    from cognitive_aim_depth_estimation_b200 import ops
+    B, S = 2, 224
+    u8 = torch.randint(0, 256, (B, S, S, 3), generator=torch.Generator().manual_seed(1235), dtype=torch.uint8)
+    mean = torch.tensor(ops.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(ops.IMAGENET_STD).view(1, 3, 1, 1)
+    ref_img = (u8.permute(0, 3, 1, 2).float() / 255.0 - mean) / std  # ToTensor + Normalize (demo.py:162-166)
+    patches = torch.zeros((B * 256, ops.PATCH_ROW_STRIDE), device=cuda_device, dtype=torch.bfloat16)
+    ops.preprocess_u8(u8.to(cuda_device), patches)
+    ref = _unfold_ref(ref_img).to(cuda_device)
+    # (x/255 - m) * (1/s) vs (x/255 - m) / s differ by 1 ulp fp32 at most -> identical after bf16 rounding except ties
+    diff = (patches[:, :588].float() - ref.bfloat16().float()).abs()
+    assert (diff <= ref.abs() * 2 ** -7).all()
+    assert (diff > 0).float().mean() < 1e-3
+
+
+@pytest.mark.parametrize("rows", [1, 37, 1370 * 3])
+def test_layernorm(cuda_device, rows):
+    from cognitive_aim_depth_estimation_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    x = (torch.randn(rows, 768, generator=g) * 3 + 1.5).to(cuda_device)
+    gamma = (torch.randn(768, generator=g) * 0.2 + 1).to(cuda_device)
+    beta = (torch.randn(768, generator=g) * 0.1).to(cuda_device)
+    ref = F.layer_norm(x, (768,), gamma, beta, 1e-6)
+    o32 = torch.empty_like(x)
+    ops.layernorm(x, gamma, beta, o32)
+    assert torch.allclose(o32, ref, rtol=1e-5, atol=2e-6)
+    o16 = torch.empty((rows, 768), device=cuda_device, dtype=torch.bfloat16)
+    ops.layernorm(x, gamma, beta, o16)
+    assert torch.equal(o16, o32.bfloat16())
+
+
+def test_cls_rows_and_focal_input(cuda_device):
+    from cognitive_aim_depth_estimation_b200 import ops
+    B, N, D = 3, 256, 768
+    g = torch.Generator().manual_seed(5)
+    tokens = torch.randn(B, N + 1, D, generator=g).to(cuda_device)
+    pe = torch.randn(N, D, generator=g).to(cuda_device)
+    rs = (torch.rand(B, N, generator=g) + 1).to(cuda_device)
+    xin = torch.empty((B * N, D), device=cuda_device, dtype=torch.bfloat16)
+    ops.focal_input(tokens, pe, rs, xin, B, N, D)
+    ref = (tokens[:, 1:] * rs.unsqueeze(-1) + pe).reshape(B * N, D)
+    assert (xin.float() - ref).abs().max() <= ref.abs().max() * 2 ** -8
+    ops.focal_input(tokens, pe, None, xin, B, N, D)
+    assert torch.equal(xin, (tokens[:, 1:] + pe).reshape(B * N, D).bfloat16())
+    cls = torch.randn(D, generator=g).to(cuda_device)
+    pos = torch.randn(N + 1, D, generator=g).to(cuda_device)
+    x = torch.zeros(B, N + 1, D, device=cuda_device)
+    ops.cls_rows(x, cls, pos, B, N + 1, D)
+    assert torch.equal(x[:, 0], (cls + pos[0]).expand(B, D))
+    assert (x[:, 1:] == 0).all()
