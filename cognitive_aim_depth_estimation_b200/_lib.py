@@ -21,6 +21,30 @@ class CogAimError(RuntimeError):
     pass
 
 
+
+
+class HeadsWeights(C.Structure):
+    """ca_heads_weights (include/cogaim_b200.h)."""
+    _names = ["amb_w0", "amb_b0", "amb_w1", "amb_b1", "amb_w2", "amb_b2", "cam_emb", "exif_w0", "exif_b0", "exif_w1",
+              "exif_b1", "exif_f0", "exif_fb0", "exif_f1", "exif_fb1", "fus_w", "fus_b", "dec_w", "dec_b", "conf_w0",
+              "conf_b0", "conf_w2", "conf_b2"]
+    _fields_ = [(n, C.c_void_p) for n in _names]
+
+
+class HeadsInputs(C.Structure):
+    """ca_heads_inputs (include/cogaim_b200.h)."""
+    _fields_ = [("tokens", C.c_void_p), ("tokens_per_img", C.c_int), ("focal_feat", C.c_void_p),
+                ("pool_partial", C.c_void_p), ("pool_splits", C.c_int), ("tmp_w", C.c_void_p), ("tmp_b", C.c_void_p),
+                ("pooled_out", C.c_void_p), ("exif", C.c_void_p), ("camera_idx", C.c_void_p)]
+
+
+class FocalValueArgs(C.Structure):
+    """ca_focal_value_args (include/cogaim_b200.h)."""
+    _fields_ = [("tok_partial", C.c_void_p), ("pe_partial", C.c_void_p), ("splits", C.c_int), ("wv", C.c_void_p),
+                ("bv", C.c_void_p), ("proj_w0", C.c_void_p), ("proj_b0", C.c_void_p), ("proj_w1", C.c_void_p),
+                ("proj_b1", C.c_void_p), ("feat_out", C.c_void_p), ("iter", C.c_int), ("n_iters", C.c_int)]
+
+
 # name -> (argtypes); every function returns int status except where noted
 _SIGNATURES = {
     "ca_version": [],
@@ -34,6 +58,13 @@ _SIGNATURES = {
     "ca_cls_rows": [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr],
     "ca_layernorm": [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr],
     "ca_focal_input": [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr],
+    "ca_rowstats_merge": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr],
+    "ca_focal_finalize": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, c_ptr],
+    "ca_guided_softmax": [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_float, C.c_float, c_ptr],
+    "ca_weighted_pool": [c_ptr, C.c_longlong, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr],
+    "ca_heads": [C.POINTER(HeadsWeights), C.POINTER(HeadsInputs), c_ptr, c_ptr, c_ptr, C.c_int, c_ptr],
+    "ca_focal_value": [C.POINTER(FocalValueArgs), C.c_int, c_ptr],
+    "ca_focal_fusion": [c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr],
 }
 
 

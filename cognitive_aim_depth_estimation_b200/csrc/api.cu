@@ -2,7 +2,9 @@
 #include "../../include/cogaim_b200.h"
 
 #include "attention.cuh"
+#include "focal.cuh"
 #include "gemm.cuh"
+#include "heads.cuh"
 #include "rowops.cuh"
 #include "host.h"
 
@@ -95,6 +97,45 @@ int ca_focal_input(const float* tokens, const float* pe, const float* rowscale, 
                    void* stream) {
   return ca::focal_input_launch(tokens, pe, rowscale, reinterpret_cast<__nv_bfloat16*>(xin), B, N, D,
                                 static_cast<cudaStream_t>(stream));
+}
+
+int ca_rowstats_merge(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, int rows, int P,
+                      void* stream) {
+  return ca::rowstats_merge_launch(pm, ps, weight, rmax, rinv, rows, P, static_cast<cudaStream_t>(stream));
+}
+
+int ca_focal_finalize(const float* pc, const float* cbias, float* attn, const float* rs_in, float* rs_out, int B, int N,
+                      int P, float focus_strength, int mode, void* stream) {
+  return ca::focal_finalize_launch(pc, cbias, attn, rs_in, rs_out, B, N, P, focus_strength, mode,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int ca_guided_softmax(const float* base, const float* mask, float* heat, int32_t* argmax, int B, int N, float alpha,
+                      float temperature, void* stream) {
+  return ca::guided_softmax_launch(base, mask, heat, argmax, B, N, alpha, temperature,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int ca_weighted_pool(const float* src, long long src_batch_stride, int row_offset, const float* w, const float* w2,
+                     float* partial, int B, int N, int D, int splits, void* stream) {
+  return ca::weighted_pool_launch(src, src_batch_stride, row_offset, w, w2, partial, B, N, D, splits,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int ca_heads(const ca_heads_weights* w, const ca_heads_inputs* in, float* depth, float* conf, float* fused_out, int B,
+             void* stream) {
+  if (!w || !in) return ca::invalid("heads: null argument struct");
+  return ca::heads_launch(*w, *in, depth, conf, fused_out, B, static_cast<cudaStream_t>(stream));
+}
+
+int ca_focal_value(const ca_focal_value_args* a, int B, void* stream) {
+  if (!a) return ca::invalid("focal_value: null argument struct");
+  return ca::focal_value_launch(*a, B, static_cast<cudaStream_t>(stream));
+}
+
+int ca_focal_fusion(const float* feats, int n_iters, const float* w0, const float* b0, const float* w1, const float* b1,
+                    float* out, int B, void* stream) {
+  return ca::focal_fusion_launch(feats, n_iters, w0, b0, w1, b1, out, B, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

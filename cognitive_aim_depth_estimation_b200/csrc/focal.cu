@@ -1,0 +1,206 @@
+// Vector-sized stages of the focal / guidance path (fp32 throughout; block reductions via warp shuffles):
+//   rowstats_merge   : merge the per-64-column softmax partials of GEMM pass A into (row max, weight / row sum)
+//   focal_finalize   : column sums of pass B -> mean + centre bias -> L1 norm -> clamp -> renorm (+ re-focus scale)
+//   guided_softmax   : softmax((0.7*mask + 0.3*a) / 0.05) and its argmax cell
+//   weighted_pool    : sum_n w[b,n] * tokens[b,1+n,:]  (bandwidth-bound, split over N, deterministic partials)
+// Reference: src/model.py:197-200,234-282 (FocalStream), :426 (re-focus), :1404-1414 (_guided_focal_stream).
+#include "common.cuh"
+#include "focal.cuh"
+#include "host.h"
+
+namespace ca {
+namespace {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = warp_id(), l = lane_id(), nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < nw) ? red[l] : 0.f;
+  t = warp_sum(t);
+  return t;  // every thread holds the total
+}
+
+// pm, ps: [rows, P] (row max / sum-exp2 per 64-column span) -> rmax[rows], rinv[rows] = weight[row] / sum
+__global__ void rowstats_merge_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
+                                      const float* __restrict__ weight, float* __restrict__ rmax,
+                                      float* __restrict__ rinv, int rows, int P) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* m = pm + static_cast<size_t>(r) * P;
+  const float* s = ps + static_cast<size_t>(r) * P;
+  float mx = -INFINITY;
+  for (int i = 0; i < P; ++i) mx = fmaxf(mx, m[i]);
+  float sum = 0.f;
+  for (int i = 0; i < P; ++i) sum += s[i] * exp2f(m[i] - mx);  // s = 0 where the span is fully masked (m = -inf)
+  rmax[r] = mx;
+  rinv[r] = (weight ? weight[r] : 1.0f) / sum;
+}
+
+// One CTA per image.  pc: [B, N, P] column-sum partials.  attn[b, j] = final_attention of the iteration.
+// rowscale_out[b, j] = rowscale_in[b, j] * (1 + focus_strength * attn)  when rowscale_out != nullptr.
+// mode 0: FocalStream attention  (mean over rows, centre bias, L1, clamp, renorm)   src/model.py:234-282
+// mode 1: plain sum of partials (weighted column sums for the un-guided value path; no bias / normalisation)
+__global__ void __launch_bounds__(256) focal_finalize_kernel(const float* __restrict__ pc, const float* __restrict__ cbias,
+                                                              float* __restrict__ attn, const float* __restrict__ rs_in,
+                                                              float* __restrict__ rs_out, int N, int P,
+                                                              float focus_strength, int mode) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* pcb = pc + static_cast<size_t>(b) * N * P;
+  float* ab = attn + static_cast<size_t>(b) * N;
+  const float invN = 1.0f / static_cast<float>(N);
+  float local = 0.f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const float* p = pcb + static_cast<size_t>(j) * P;
+    float s = 0.f;
+    for (int i = 0; i < P; ++i) s += p[i];
+    const float v = (mode == 0) ? (s * invN + cbias[j]) : s;
+    ab[j] = v;
+    local += v;
+  }
+  if (mode != 0) return;
+  const float tot1 = block_sum(local, red);
+  const float d1 = tot1 + 1e-8f;
+  local = 0.f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const float v = fmaxf(ab[j] / d1, 1e-8f);
+    ab[j] = v;
+    local += v;
+  }
+  const float tot2 = block_sum(local, red);
+  const float d2 = tot2 + 1e-8f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const float a = ab[j] / d2;
+    ab[j] = a;
+    if (rs_out) {
+      const size_t o = static_cast<size_t>(b) * N + j;
+      rs_out[o] = (rs_in ? rs_in[o] : 1.0f) * (1.0f + focus_strength * a);
+    }
+  }
+}
+
+// heat[b, :] = softmax((alpha*mask + (1-alpha)*base[b, :]) / temperature), argmax[b] = first index of the maximum
+__global__ void __launch_bounds__(256) guided_softmax_kernel(const float* __restrict__ base, const float* __restrict__ mask,
+                                                              float* __restrict__ heat, int* __restrict__ argmax, int N,
+                                                              float alpha, float temperature) {
+  __shared__ float red[32];
+  __shared__ int redi[32];
+  const int b = blockIdx.x;
+  const float* bb = base + static_cast<size_t>(b) * N;
+  float* hb = heat + static_cast<size_t>(b) * N;
+  float mx = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const float t = (alpha * mask[j] + (1.0f - alpha) * bb[j]) / temperature;
+    hb[j] = t;
+    if (t > mx) {
+      mx = t;
+      mi = j;
+    }
+  }
+  // block arg-max with first-index tie-break
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > mx || (om == mx && oi < mi)) {
+      mx = om;
+      mi = oi;
+    }
+  }
+  const int w = warp_id(), l = lane_id(), nw = blockDim.x >> 5;
+  if (l == 0) {
+    red[w] = mx;
+    redi[w] = mi;
+  }
+  __syncthreads();
+  mx = (l < nw) ? red[l] : -INFINITY;
+  mi = (l < nw) ? redi[l] : 0x7fffffff;
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > mx || (om == mx && oi < mi)) {
+      mx = om;
+      mi = oi;
+    }
+  }
+  float local = 0.f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const float e = expf(hb[j] - mx);
+    hb[j] = e;
+    local += e;
+  }
+  const float tot = block_sum(local, red);
+  for (int j = threadIdx.x; j < N; j += blockDim.x) hb[j] = hb[j] / tot;
+  if (threadIdx.x == 0 && argmax) argmax[b] = mi;
+}
+
+// partial[b, split, :] = sum_{n in split} w[b, n] * (w2 ? w2[b, n] : 1) * src[b*src_batch_stride + (row_offset+n)*D + :]
+// D = 768: 192 threads x float4.  grid = (splits, B).
+__global__ void __launch_bounds__(192) weighted_pool_kernel(const float* __restrict__ src, long long src_batch_stride,
+                                                             int row_offset, const float* __restrict__ w,
+                                                             const float* __restrict__ w2, float* __restrict__ partial,
+                                                             int N, int D, int rows_per_split) {
+  const int b = blockIdx.y;
+  const int split = blockIdx.x;
+  const int n0 = split * rows_per_split;
+  const int n1 = min(N, n0 + rows_per_split);
+  const float4* s4 = reinterpret_cast<const float4*>(src + static_cast<size_t>(b) * src_batch_stride +
+                                                     static_cast<size_t>(row_offset) * D);
+  const float* wb = w + static_cast<size_t>(b) * N;
+  const float* w2b = w2 ? w2 + static_cast<size_t>(b) * N : nullptr;
+  const int dv = D / 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int n = n0; n < n1; ++n) {
+    float g = wb[n];
+    if (w2b) g *= w2b[n];
+    const float4 t = s4[static_cast<size_t>(n) * dv + threadIdx.x];
+    acc.x = fmaf(g, t.x, acc.x);
+    acc.y = fmaf(g, t.y, acc.y);
+    acc.z = fmaf(g, t.z, acc.z);
+    acc.w = fmaf(g, t.w, acc.w);
+  }
+  reinterpret_cast<float4*>(partial + (static_cast<size_t>(b) * gridDim.x + split) * D)[threadIdx.x] = acc;
+}
+
+}  // namespace
+
+int rowstats_merge_launch(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, int rows,
+                          int P, cudaStream_t stream) {
+  CA_REQUIRE(pm && ps && rmax && rinv, "rowstats_merge: null pointer");
+  rowstats_merge_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(pm, ps, weight, rmax, rinv, rows, P);
+  CA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int focal_finalize_launch(const float* pc, const float* cbias, float* attn, const float* rs_in, float* rs_out, int B,
+                          int N, int P, float focus_strength, int mode, cudaStream_t stream) {
+  CA_REQUIRE(pc && attn, "focal_finalize: null pointer");
+  CA_REQUIRE(mode != 0 || cbias, "focal_finalize: null centre bias");
+  focal_finalize_kernel<<<B, 256, 0, stream>>>(pc, cbias, attn, rs_in, rs_out, N, P, focus_strength, mode);
+  CA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int guided_softmax_launch(const float* base, const float* mask, float* heat, int* argmax, int B, int N, float alpha,
+                          float temperature, cudaStream_t stream) {
+  CA_REQUIRE(base && mask && heat, "guided_softmax: null pointer");
+  guided_softmax_kernel<<<B, 256, 0, stream>>>(base, mask, heat, argmax, N, alpha, temperature);
+  CA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int weighted_pool_launch(const float* src, long long src_batch_stride, int row_offset, const float* w, const float* w2,
+                         float* partial, int B, int N, int D, int splits, cudaStream_t stream) {
+  CA_REQUIRE(src && w && partial, "weighted_pool: null pointer");
+  CA_REQUIRE(D == 768, "weighted_pool: only D = 768 is instantiated");
+  CA_REQUIRE(splits > 0, "weighted_pool: splits must be positive");
+  const int rps = (N + splits - 1) / splits;
+  weighted_pool_kernel<<<dim3(splits, B), 192, 0, stream>>>(src, src_batch_stride, row_offset, w, w2, partial, N, D, rps);
+  CA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ca

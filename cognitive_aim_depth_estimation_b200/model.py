@@ -1,0 +1,561 @@
+"""Host-side mirror of the reference's model surface (reference src/model.py), driving the sm_100a kernels.
+
+`create_model(config, camera_info, device)` returns a `CognitiveAimModel` whose `forward` /
+`forward_with_guidance` / `get_attention_weights` / `get_features` signatures, return shapes, side effects
+(`_last_attention_weights`, `fusion_features`) and `state_dict()` names match the reference (src/model.py:1064,
+1157, 1058, 1428, 1534), so `demo.py` can switch imports and keep working.
+
+Differences that are deliberate:
+  * the forward runs ONLY on a CUDA sm_100 device through libcogaim_b200.so; there is no CPU fallback and errors
+    are raised, never swallowed (the reference prints and falls back, src/model.py:1050-1056,1237-1240);
+  * the reference's redundant passes (backbone x3, focal stream x4 in `forward`) are computed once;
+  * output-dead work of the effective configuration (value path / projections in guided mode, CuriosityModule
+    score, DimensionAligners, LoRA) is not executed; the CuriosityModule's two `randn_like` draws are replayed on
+    the CPU generator so that the per-call random projection (src/model.py:1421) matches the reference under a
+    shared `torch.manual_seed`.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops, tables
+from .config import DEFAULT_COGNITIVE_MODULES, EffectiveConfig, effective_config
+
+_D = 768
+_HEADS = 12
+_LAYERS = 12
+_MLP = 3072
+_POOL_SPLITS = 8
+
+
+# ------------------------------------------------------------------------------------------------------
+# Parameter tree with the reference's state_dict names
+# ------------------------------------------------------------------------------------------------------
+
+def _param_specs(cfg: EffectiveConfig):
+    """(name, shape, kind) in reference state_dict order; kind in {w, b, ones, zeros, const:<v>, buf...}."""
+    s = []
+    e = "backbone.embeddings."
+    s += [(e + "cls_token", (1, 1, _D), "w"), (e + "mask_token", (1, _D), "zeros"),
+          (e + "position_embeddings", (1, 1370, _D), "w"),
+          (e + "patch_embeddings.projection.weight", (_D, 3, 14, 14), "w"),
+          (e + "patch_embeddings.projection.bias", (_D,), "zeros")]
+    for i in range(_LAYERS):
+        p = f"backbone.encoder.layer.{i}."
+        s += [(p + "norm1.weight", (_D,), "ones"), (p + "norm1.bias", (_D,), "zeros")]
+        for n in ("query", "key", "value"):
+            s += [(p + f"attention.attention.{n}.weight", (_D, _D), "w"),
+                  (p + f"attention.attention.{n}.bias", (_D,), "zeros")]
+        s += [(p + "attention.output.dense.weight", (_D, _D), "w"), (p + "attention.output.dense.bias", (_D,), "zeros"),
+              (p + "layer_scale1.lambda1", (_D,), "ones"),
+              (p + "norm2.weight", (_D,), "ones"), (p + "norm2.bias", (_D,), "zeros"),
+              (p + "mlp.fc1.weight", (_MLP, _D), "w"), (p + "mlp.fc1.bias", (_MLP,), "zeros"),
+              (p + "mlp.fc2.weight", (_D, _MLP), "w"), (p + "mlp.fc2.bias", (_D,), "zeros"),
+              (p + "layer_scale2.lambda1", (_D,), "ones")]
+    s += [("backbone.layernorm.weight", (_D,), "ones"), ("backbone.layernorm.bias", (_D,), "zeros")]
+
+    def lin(name, o, i):
+        return [(name + ".weight", (o, i), "w"), (name + ".bias", (o,), "zeros")]
+
+    s += lin("ambient_stream.mlp.0", 256, _D) + lin("ambient_stream.mlp.3", 128, 256) + lin("ambient_stream.mlp.5", 64, 128)
+    h = cfg.focal_hidden_dim
+    s += [("focal_stream.initial_focus", (1, _D), "w")]
+    for i in range(cfg.num_iterations):
+        p = f"focal_stream.focal_streams.{i}."
+        s += [(p + "adaptive_weight", (), "const:0.5")]
+        s += lin(p + "query_proj", _D, _D) + lin(p + "key_proj", _D, _D) + lin(p + "value_proj", _D, _D)
+        s += lin(p + "projection.0", h, _D) + lin(p + "projection.3", h // 4, h)
+    s += lin("focal_stream.fusion.0", h // 2, h // 4 * cfg.num_iterations) + lin("focal_stream.fusion.2", h // 4, h // 2)
+    if cfg.use_exif:
+        s += [("exif_prior.camera_embedding.weight", (cfg.num_cameras, 64), "w")]
+        s += lin("exif_prior.exif_encoder.0", 64, 3) + lin("exif_prior.exif_encoder.2", 64, 64)
+        s += lin("exif_prior.fusion.0", 256, 128) + lin("exif_prior.fusion.3", 64, 256)
+    s += lin("fusion.0", 192, 192)
+    for n in ("ambient", "focal", "exif"):
+        s += lin(f"{n}_dim_aligner.projection", _D, 64)
+    s += [("decision_head.0.weight", (1, 192), "w"), ("decision_head.0.bias", (1,), "const:1.0")]
+    s += lin("confidence_head.0", 1, 192)
+    s += [("confidence_head.2.weight", (1, 1), "const:0.5"), ("confidence_head.2.bias", (1,), "const:2.0")]
+    c = "curiosity_module."
+    s += [(c + "curiosity_weights", (3,), "curw"), (c + "exploration_history", (1000,), "buf_zeros"),
+          (c + "history_pointer", (), "buf_long")]
+    s += lin(c + "encoder_mean.0", 384, _D) + lin(c + "encoder_mean.3", 192, 384)
+    s += lin(c + "encoder_logvar.0", 384, _D) + lin(c + "encoder_logvar.3", 192, 384)
+    s += lin(c + "decoder.0", 384, 192) + lin(c + "decoder.3", 192, 384)
+    s += lin(c + "uncertainty_head.0", 192, _D) + lin(c + "uncertainty_head.2", 1, 192)
+    if cfg.enable_hierarchical_curiosity:
+        s += lin(c + "geometric_curiosity.0", 256, _D + 4) + lin(c + "geometric_curiosity.2", 1, 256)
+        s += lin(c + "local_curiosity.0", 128, _D) + lin(c + "local_curiosity.2", 1, 128)
+    s += lin("global_aligner.projection", _D, 3 * _D)
+    return s
+
+
+def _register(root: nn.Module, dotted: str, tensor: torch.Tensor, buffer: bool):
+    mod = root
+    parts = dotted.split(".")
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, nn.Module())
+        mod = mod._modules[p]
+    if buffer:
+        mod.register_buffer(parts[-1], tensor)
+    else:
+        mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+class CognitiveAimModel(nn.Module):
+    """Drop-in for the reference `CognitiveAimModel` (inference only)."""
+
+    def __init__(self, config: dict, camera_info: Optional[dict] = None):
+        super().__init__()
+        self.config = config
+        cfg = effective_config(config, camera_info)
+        self.cfg = cfg
+        if cfg.backbone_size != "base":
+            raise NotImplementedError("only the DINOv2 ViT-B/14 backbone (backbone_size='base') is built")
+        if not (cfg.use_ambient and cfg.use_iterative):
+            raise NotImplementedError(
+                "the B200 path is built for the configuration every shipped YAML resolves to "
+                "(ambient_stream + iterative_focal_stream [+ exif_prior_database]); got cognitive_modules without them")
+        if cfg.curiosity_guided:
+            raise NotImplementedError("curiosity_guided_attention.enabled=True is not built (SURVEY.md §8f rank 4)")
+        # attributes demo.py reads (demo.py:71-73,380-382)
+        self.backbone_size = cfg.backbone_size
+        self.feature_dim = cfg.feature_dim
+        self.fusion_dim = cfg.fusion_dim
+        self.use_lora = cfg.use_lora  # LoRA is dead code in the reference (quirk 4): flag kept, nothing executed
+        self.use_ambient, self.use_focal = cfg.use_ambient, cfg.use_focal
+        self.use_iterative, self.use_exif = cfg.use_iterative, cfg.use_exif
+        self.target_fusion_dim = 768
+        gen = torch.Generator().manual_seed(0x5EED)
+        for name, shape, kind in _param_specs(cfg):
+            if kind == "w":
+                t = torch.empty(shape).normal_(0.0, 0.02, generator=gen).clamp_(-0.04, 0.04)
+            elif kind == "ones":
+                t = torch.ones(shape)
+            elif kind == "zeros":
+                t = torch.zeros(shape)
+            elif kind.startswith("const:"):
+                t = torch.full(shape, float(kind[6:]))
+            elif kind == "curw":
+                t = torch.tensor([0.4, 0.3, 0.3])
+            elif kind == "buf_zeros":
+                t = torch.zeros(shape)
+            elif kind == "buf_long":
+                t = torch.tensor(0)
+            else:
+                raise AssertionError(kind)
+            _register(self, name, t, buffer=kind.startswith("buf"))
+        self._packed = None       # device-side packed weights (bf16 GEMM operands etc.)
+        self._packed_key = None
+        self._tables: Dict = {}   # per-grid tables (pos-embed, PE, centre bias, masks)
+        self._ws: Dict = {}       # workspaces keyed by (B, S)
+        self.validate_inputs = True
+        self.eval()
+
+    # -- nn.Module protocol -----------------------------------------------------------------------------
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("inference-only implementation: training mode is not built")
+        return super().train(False)
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        self._invalidate()
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
+
+    def _invalidate(self):
+        self._packed = None
+        self._tables = {}
+        self._ws = {}
+
+    def _sd(self) -> Dict[str, torch.Tensor]:
+        return dict(self.state_dict(keep_vars=True))
+
+    # -- weight packing ---------------------------------------------------------------------------------
+    def _device(self) -> torch.device:
+        return self.backbone.layernorm.weight.device
+
+    def _pack(self):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError(
+                "CognitiveAimModel runs only on a CUDA sm_100 device (call .to('cuda')); there is no CPU fallback")
+        if self._packed is not None:
+            return self._packed
+        ops._lib.check(ops._lib.load().ca_device_check(dev.index or 0), "ca_device_check")
+        sd = {k: v.detach() for k, v in self._sd().items()}
+        f32 = lambda t: t.to(dev, torch.float32).contiguous()  # noqa: E731
+        b16 = lambda t: t.to(dev, torch.bfloat16).contiguous()  # noqa: E731
+        pk = {}
+        e = "backbone.embeddings."
+        wpe = torch.zeros(_D, ops.PATCH_ROW_STRIDE, device=dev, dtype=torch.bfloat16)
+        wpe[:, :588] = b16(sd[e + "patch_embeddings.projection.weight"].reshape(_D, 588))
+        pk["patch_w"], pk["patch_b"] = wpe, f32(sd[e + "patch_embeddings.projection.bias"])
+        pk["cls"] = f32(sd[e + "cls_token"].reshape(_D))
+        layers = []
+        for i in range(_LAYERS):
+            p = f"backbone.encoder.layer.{i}."
+            a = p + "attention.attention."
+            L = {
+                "n1w": f32(sd[p + "norm1.weight"]), "n1b": f32(sd[p + "norm1.bias"]),
+                "wqkv": b16(torch.cat([sd[a + "query.weight"], sd[a + "key.weight"], sd[a + "value.weight"]], 0)),
+                "bqkv": f32(torch.cat([sd[a + "query.bias"], sd[a + "key.bias"], sd[a + "value.bias"]], 0)),
+                "wo": b16(sd[p + "attention.output.dense.weight"]), "bo": f32(sd[p + "attention.output.dense.bias"]),
+                "ls1": f32(sd[p + "layer_scale1.lambda1"]),
+                "n2w": f32(sd[p + "norm2.weight"]), "n2b": f32(sd[p + "norm2.bias"]),
+                "w1": b16(sd[p + "mlp.fc1.weight"]), "b1": f32(sd[p + "mlp.fc1.bias"]),
+                "w2": b16(sd[p + "mlp.fc2.weight"]), "b2": f32(sd[p + "mlp.fc2.bias"]),
+                "ls2": f32(sd[p + "layer_scale2.lambda1"]),
+            }
+            layers.append(L)
+        pk["layers"] = layers
+        pk["lnw"], pk["lnb"] = f32(sd["backbone.layernorm.weight"]), f32(sd["backbone.layernorm.bias"])
+        focal = []
+        for i in range(self.cfg.num_iterations):
+            p = f"focal_stream.focal_streams.{i}."
+            focal.append({
+                "wqk": b16(torch.cat([sd[p + "query_proj.weight"], sd[p + "key_proj.weight"]], 0)),
+                "bqk": f32(torch.cat([sd[p + "query_proj.bias"], sd[p + "key_proj.bias"]], 0)),
+                "wv": f32(sd[p + "value_proj.weight"]), "bv": f32(sd[p + "value_proj.bias"]),
+                "pw0": f32(sd[p + "projection.0.weight"]), "pb0": f32(sd[p + "projection.0.bias"]),
+                "pw1": f32(sd[p + "projection.3.weight"]), "pb1": f32(sd[p + "projection.3.bias"]),
+            })
+        pk["focal"] = focal
+        pk["ffw0"], pk["ffb0"] = f32(sd["focal_stream.fusion.0.weight"]), f32(sd["focal_stream.fusion.0.bias"])
+        pk["ffw1"], pk["ffb1"] = f32(sd["focal_stream.fusion.2.weight"]), f32(sd["focal_stream.fusion.2.bias"])
+        z = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
+        if self.use_exif:
+            ex = {"cam_emb": f32(sd["exif_prior.camera_embedding.weight"]),
+                  "exif_w0": f32(sd["exif_prior.exif_encoder.0.weight"]), "exif_b0": f32(sd["exif_prior.exif_encoder.0.bias"]),
+                  "exif_w1": f32(sd["exif_prior.exif_encoder.2.weight"]), "exif_b1": f32(sd["exif_prior.exif_encoder.2.bias"]),
+                  "exif_f0": f32(sd["exif_prior.fusion.0.weight"]), "exif_fb0": f32(sd["exif_prior.fusion.0.bias"]),
+                  "exif_f1": f32(sd["exif_prior.fusion.3.weight"]), "exif_fb1": f32(sd["exif_prior.fusion.3.bias"])}
+        else:
+            ex = {"cam_emb": z(1, 64), "exif_w0": z(64, 3), "exif_b0": z(64), "exif_w1": z(64, 64), "exif_b1": z(64),
+                  "exif_f0": z(256, 128), "exif_fb0": z(256), "exif_f1": z(64, 256), "exif_fb1": z(64)}
+        hw = {
+            "amb_w0": f32(sd["ambient_stream.mlp.0.weight"]), "amb_b0": f32(sd["ambient_stream.mlp.0.bias"]),
+            "amb_w1": f32(sd["ambient_stream.mlp.3.weight"]), "amb_b1": f32(sd["ambient_stream.mlp.3.bias"]),
+            "amb_w2": f32(sd["ambient_stream.mlp.5.weight"]), "amb_b2": f32(sd["ambient_stream.mlp.5.bias"]),
+            **ex,
+            "fus_w": f32(sd["fusion.0.weight"]), "fus_b": f32(sd["fusion.0.bias"]),
+            "dec_w": f32(sd["decision_head.0.weight"]), "dec_b": f32(sd["decision_head.0.bias"]),
+            "conf_w0": f32(sd["confidence_head.0.weight"]), "conf_b0": f32(sd["confidence_head.0.bias"]),
+            "conf_w2": f32(sd["confidence_head.2.weight"]), "conf_b2": f32(sd["confidence_head.2.bias"]),
+        }
+        pk["heads_tensors"] = hw
+        pk["heads"] = ops.make_heads_weights(hw)
+        pk["pos_param"] = sd[e + "position_embeddings"]
+        self._packed = pk
+        return pk
+
+    def _grid_tables(self, g: int):
+        dev = self._device()
+        t = self._tables.get(g)
+        if t is None:
+            if g < 4:
+                raise ValueError("patch grids smaller than 4 x 4 are not supported (the reference's degenerate-variance "
+                                 "fallbacks, src/model.py:242-257, are not built)")
+            n = g * g
+            pk = self._pack()
+            t = {"pos": tables.interpolate_pos_embed(pk["pos_param"], g).to(dev),
+                 "pe": tables.focal_position_encoding(n, _D).to(dev),
+                 "cbias": tables.center_bias(n).to(dev), "masks": {}}
+            self._tables[g] = t
+        return t
+
+    def _mask(self, guidance, g: int) -> torch.Tensor:
+        t = self._grid_tables(g)
+        if isinstance(guidance, str):
+            key = tables.canonical_instruction(guidance)
+            m = t["masks"].get(key)
+            if m is None:
+                m = tables.resolve_guidance(guidance, g * g).to(self._device())
+                t["masks"][key] = m
+            return m
+        return tables.resolve_guidance(guidance, g * g).to(self._device())
+
+    def _workspace(self, B: int, S: int):
+        key = (B, S)
+        ws = self._ws.get(key)
+        if ws is None:
+            dev = self._device()
+            g = S // 14
+            N, T = g * g, g * g + 1
+            P = ops.stats_partials(N)
+            bf = dict(device=dev, dtype=torch.bfloat16)
+            fl = dict(device=dev, dtype=torch.float32)
+            ws = {
+                "patches": torch.empty(B * N, ops.PATCH_ROW_STRIDE, **bf),
+                "x": torch.empty(B * T, _D, **fl), "h": torch.empty(B * T, _D, **bf),
+                "qkv": torch.empty(B * T, 3 * _D, **bf), "att": torch.empty(B * T, _D, **bf),
+                "mlp": torch.empty(B * T, _MLP, **bf), "tokens": torch.empty(B, T, _D, **fl),
+                "xin": torch.empty(B * N, _D, **bf), "qk": torch.empty(B * N, 2 * _D, **bf),
+                "pm": torch.empty(B, N, P, **fl), "ps": torch.empty(B, N, P, **fl), "pc": torch.empty(B, N, P, **fl),
+                "rmax": torch.empty(B, N, **fl), "rinv": torch.empty(B, N, **fl),
+                "attn": torch.empty(self.cfg.num_iterations, B, N, **fl), "cvec": torch.empty(B, N, **fl),
+                "rowscale": torch.empty(2, B, N, **fl),
+                "heat": torch.empty(B, N, **fl), "argmax": torch.empty(B, device=dev, dtype=torch.int32),
+                "pool": torch.empty(B, _POOL_SPLITS, _D, **fl), "pool_pe": torch.empty(B, _POOL_SPLITS, _D, **fl),
+                "pooled": torch.empty(B, _D, **fl), "feats": torch.empty(B, self.cfg.num_iterations, 64, **fl),
+                "focal_feat": torch.empty(B, 64, **fl), "fused": torch.empty(B, 192, **fl),
+                "depth": torch.empty(B, **fl), "conf": torch.empty(B, **fl),
+            }
+            if len(self._ws) >= 4:  # keep the cache bounded
+                self._ws.pop(next(iter(self._ws)))
+            self._ws[key] = ws
+        return ws
+
+    # -- stages -----------------------------------------------------------------------------------------
+    @staticmethod
+    def _check_images(images):
+        if not torch.is_tensor(images) or images.dim() != 4 or images.shape[1] != 3:
+            raise ValueError("images must be a [B, 3, S, S] tensor")
+        B, _, H, W = images.shape
+        if H != W or H < 56:
+            raise ValueError(f"images must be square with side >= 56 (got {H} x {W})")
+        if not images.is_floating_point():
+            raise ValueError("images must be floating point (already normalised); use preprocess_u8 for uint8 HWC input")
+        return B, H
+
+    def backbone_tokens(self, images: torch.Tensor, *, patches: Optional[torch.Tensor] = None, B=None, S=None):
+        """DINOv2 ViT-B/14 `last_hidden_state` [B, 1+N, 768] fp32 (HF modeling_dinov2.py:459-485).
+        `patches` (bf16 [B*N, 592] from `preprocess_u8`) may be given instead of images."""
+        pk = self._pack()
+        dev = self._device()
+        if patches is None:
+            B, S = self._check_images(images)
+            images = images.to(dev, torch.float32).contiguous()
+        g = S // 14
+        N, T = g * g, g * g + 1
+        ws = self._workspace(B, S)
+        tb = self._grid_tables(g)
+        if patches is None:
+            patches = ops.patchify_f32(images, ws["patches"])
+        x, h = ws["x"], ws["h"]
+        ops.cls_rows(x, pk["cls"], tb["pos"], B, T, _D)
+        ops.gemm(patches, pk["patch_w"], ops.EPI_PATCH_F32, x, bias=pk["patch_b"], pos=tb["pos"], patches_per_img=N)
+        for L in pk["layers"]:
+            ops.layernorm(x, L["n1w"], L["n1b"], h)
+            ops.gemm(h, L["wqkv"], ops.EPI_BIAS_BF16, ws["qkv"], bias=L["bqkv"])
+            ops.attention(ws["qkv"], ws["att"], B, T, _HEADS)
+            ops.gemm(ws["att"], L["wo"], ops.EPI_RESID_F32, x, bias=L["bo"], ls=L["ls1"])
+            ops.layernorm(x, L["n2w"], L["n2b"], h)
+            ops.gemm(h, L["w1"], ops.EPI_GELU_BF16, ws["mlp"], bias=L["b1"])
+            ops.gemm(ws["mlp"], L["w2"], ops.EPI_RESID_F32, x, bias=L["b2"], ls=L["ls2"])
+        ops.layernorm(x, pk["lnw"], pk["lnb"], ws["tokens"].view(B * T, _D))
+        return ws["tokens"]
+
+    def _focal_iterations(self, ws, B: int, g: int, want_features: bool):
+        """IterativeFocalStream (src/model.py:391-455): per iteration Q|K projection, two tensor-core passes over
+        Q K^T (row statistics, then column sums in the transposed orientation) and the vector epilogue.
+        Returns the last iteration's attention [B, N]; fills ws['focal_feat'] when `want_features`."""
+        pk = self._pack()
+        tb = self._grid_tables(g)
+        N = g * g
+        scale_log2 = ops.LOG2E / math.sqrt(_D // 8)  # src/model.py:69 (single head, sqrt(768 // 8))
+        iters = self.cfg.num_iterations
+        qk = ws["qk"]
+        q, k = qk[:, :_D], qk[:, _D:]
+        rs = None
+        for i in range(iters):
+            F_ = pk["focal"][i]
+            ops.focal_input(ws["tokens"], tb["pe"], rs, ws["xin"], B, N, _D)
+            ops.gemm(ws["xin"], F_["wqk"], ops.EPI_BIAS_BF16, qk, bias=F_["bqk"])
+            common = dict(M=N, N=N, K=_D, lda=2 * _D, ldw=2 * _D, batch=B, a_batch_stride=N * 2 * _D,
+                          w_batch_stride=N * 2 * _D, scale_log2=scale_log2)
+            ops.gemm(q, k, ops.EPI_ROWSTATS, None, part_a=ws["pm"], part_b=ws["ps"], **common)
+            ops.rowstats_merge(ws["pm"], ws["ps"], None, ws["rmax"], ws["rinv"])
+            ops.gemm(k, q, ops.EPI_COLSUM, None, part_a=ws["pc"], col_max=ws["rmax"], col_rinv=ws["rinv"], **common)
+            last = i == iters - 1
+            rs_out = None if last else ws["rowscale"][i % 2]
+            ops.focal_finalize(ws["pc"], tb["cbias"], ws["attn"][i], rs, rs_out, B, N, self.cfg.focus_strength, 0)
+            if want_features:
+                # value path re-associated: sum_i a_i (A V)_i = ((a^T A) x~) Wv^T + bv   (src/model.py:204,308)
+                ops.rowstats_merge(ws["pm"], ws["ps"], ws["attn"][i], ws["rmax"], ws["rinv"])
+                ops.gemm(k, q, ops.EPI_COLSUM, None, part_a=ws["pc"], col_max=ws["rmax"], col_rinv=ws["rinv"], **common)
+                ops.focal_finalize(ws["pc"], None, ws["cvec"], None, None, B, N, 0.0, 1)
+                T = N + 1
+                ops.weighted_pool(ws["tokens"], T * _D, 1, ws["cvec"], rs, ws["pool"], B, N, _D, _POOL_SPLITS)
+                ops.weighted_pool(tb["pe"], 0, 0, ws["cvec"], None, ws["pool_pe"], B, N, _D, _POOL_SPLITS)
+                ops.focal_value(tok_partial=ws["pool"], pe_partial=ws["pool_pe"], splits=_POOL_SPLITS, wv=F_["wv"],
+                                bv=F_["bv"], proj_w0=F_["pw0"], proj_b0=F_["pb0"], proj_w1=F_["pw1"], proj_b1=F_["pb1"],
+                                feat_out=ws["feats"], it=i, n_iters=iters, B=B)
+            rs = rs_out
+        if want_features:
+            ops.focal_fusion(ws["feats"], iters, pk["ffw0"], pk["ffb0"], pk["ffw1"], pk["ffb1"], ws["focal_feat"], B)
+        return ws["attn"][iters - 1]
+
+    def _exif_tensors(self, exif_data, B: int):
+        if exif_data is None or not self.use_exif:
+            return None, None
+        dev = self._device()
+
+        def flat(key, dtype):
+            if key not in exif_data:
+                raise ValueError(f"exif_data is missing '{key}'")
+            t = exif_data[key]
+            if not torch.is_tensor(t):
+                t = torch.as_tensor(t)
+            t = t.reshape(-1).to(dev, dtype)
+            if t.numel() != B:
+                raise ValueError(f"exif_data['{key}'] has {t.numel()} entries for a batch of {B}")
+            return t
+
+        cont = torch.stack([flat("focal_length", torch.float32), flat("aperture", torch.float32),
+                            flat("iso", torch.float32)], dim=1).contiguous()
+        cam = flat("camera_idx", torch.int64).contiguous()
+        if self.validate_inputs and (int(cam.min()) < 0 or int(cam.max()) >= self.cfg.num_cameras):
+            raise ValueError("camera_idx out of range")  # (one tiny D2H sync; disable for CUDA-graph capture)
+        return cont, cam
+
+    @staticmethod
+    def _replay_reference_rng(B: int):
+        """CuriosityModule draws randn(B,192) then randn(B,768) on the global CPU generator in eval
+        (src/model.py:609,744) before the per-call projection is initialised (:1421)."""
+        torch.randn(B, 192)
+        torch.randn(B, 768)
+
+    # -- public forward passes --------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_with_guidance(self, images, exif_data=None, attention_guidance=None, return_attention=False):
+        """reference src/model.py:1157-1240.  Returns (depth [B,1], confidence [B,1][, attention [B,N]])."""
+        if attention_guidance is None and exif_data is not None and self.use_exif:
+            # guidance None -> plain focal-stream features and attention (:1206-1212)
+            return self._forward_impl(images, exif_data, return_attention, keep_last=False)
+        if exif_data is None or not self.use_exif:
+            # reference: the 128-wide concat fails inside `fusion`, the except branch falls back to forward()
+            # (:1237-1240) AFTER the guided attention was stored at :1212 — reproduce exactly that end state.
+            out = self._forward_impl(images, exif_data, return_attention, keep_last=True)
+            if attention_guidance is not None:
+                B, S = self._check_images(images)
+                g = S // 14
+                ws = self._workspace(B, S)
+                ops.guided_softmax(ws["attn"][self.cfg.num_iterations - 1], self._mask(attention_guidance, g),
+                                   ws["heat"], ws["argmax"], B, g * g)
+                self._last_attention_weights = ws["heat"].clone()
+            return out
+        B, S = self._check_images(images)
+        pk = self._pack()
+        dev = self._device()
+        g = S // 14
+        N, T = g * g, g * g + 1
+        mask = self._mask(attention_guidance, g)
+        exif, cam = self._exif_tensors(exif_data, B)
+        self._replay_reference_rng(B)
+        tmp = nn.Linear(_D, 64)  # same constructor => same CPU-generator draws as src/model.py:1421
+        tmp_w = tmp.weight.detach().to(dev, non_blocking=True)
+        tmp_b = tmp.bias.detach().to(dev, non_blocking=True)
+        ws = self._workspace(B, S)
+        self.backbone_tokens(images)
+        base = self._focal_iterations(ws, B, g, want_features=False)
+        ops.guided_softmax(base, mask, ws["heat"], ws["argmax"], B, N)
+        ops.weighted_pool(ws["tokens"], T * _D, 1, ws["heat"], None, ws["pool"], B, N, _D, _POOL_SPLITS)
+        ops.heads(pk["heads"], tokens=ws["tokens"], tokens_per_img=T, depth=ws["depth"], conf=ws["conf"], B=B,
+                  pool_partial=ws["pool"], pool_splits=_POOL_SPLITS, tmp_w=tmp_w, tmp_b=tmp_b,
+                  pooled_out=ws["pooled"], exif=exif, camera_idx=cam)
+        # keep the temporaries referenced until the next call (their kernels are enqueued, not finished)
+        self._keepalive = (tmp_w, tmp_b, exif, cam, mask)
+        heat = ws["heat"].clone()
+        self._last_attention_weights = heat  # :1212
+        self._last_argmax = ws["argmax"].clone()
+        depth, conf = ws["depth"].clone().unsqueeze(1), ws["conf"].clone().unsqueeze(1)
+        return (depth, conf, heat) if return_attention else (depth, conf)
+
+    @torch.no_grad()
+    def forward(self, images, exif_data=None, return_attention=False):
+        """reference src/model.py:1064-1155 (un-guided).  One backbone + one focal pass instead of 3 + 4."""
+        return self._forward_impl(images, exif_data, return_attention, keep_last=True)
+
+    def _forward_impl(self, images, exif_data, return_attention, keep_last):
+        B, S = self._check_images(images)
+        pk = self._pack()
+        g = S // 14
+        T = g * g + 1
+        exif, cam = self._exif_tensors(exif_data, B)
+        self._replay_reference_rng(B)
+        ws = self._workspace(B, S)
+        self.backbone_tokens(images)
+        att = self._focal_iterations(ws, B, g, want_features=True)
+        ops.heads(pk["heads"], tokens=ws["tokens"], tokens_per_img=T, depth=ws["depth"], conf=ws["conf"], B=B,
+                  focal_feat=ws["focal_feat"], exif=exif, camera_idx=cam, fused_out=ws["fused"])
+        self._keepalive = (exif, cam)
+        att = att.clone()
+        self.fusion_features = ws["fused"].clone()  # :1089
+        if keep_last:
+            if not hasattr(self, "_last_attention_weights"):  # :1093-1113 only set when absent
+                self._last_attention_weights = att
+        else:
+            self._last_attention_weights = att  # forward_with_guidance(..., guidance=None) always stores (:1212)
+        depth, conf = ws["depth"].clone().unsqueeze(1), ws["conf"].clone().unsqueeze(1)
+        return (depth, conf, att) if return_attention else (depth, conf)
+
+    # -- accessors ----------------------------------------------------------------------------------------
+    def get_attention_weights(self):
+        """reference src/model.py:1058-1062."""
+        return getattr(self, "_last_attention_weights", None)
+
+    @torch.no_grad()
+    def get_features_aligned(self, images, exif_data=None):
+        """[B, 192] fused features (reference src/model.py:960-1048)."""
+        self._forward_impl(images, exif_data, False, keep_last=True)
+        return self.fusion_features
+
+    def get_features(self, images, exif_data=None):
+        """reference src/model.py:1428-1430."""
+        return self.get_features_aligned(images, exif_data)
+
+    @torch.no_grad()
+    def focal_attention(self, tokens: torch.Tensor, want_features: bool = False):
+        """IterativeFocalStream on given backbone tokens [B, 1+N, 768] fp32 (test / analysis hook): returns the
+        last-iteration attention [B, N] (and the fused 64-d focal features when `want_features`)."""
+        if tokens.dim() != 3 or tokens.shape[-1] != _D:
+            raise ValueError("tokens must be [B, 1+N, 768]")
+        B, T, _ = tokens.shape
+        g = int(math.isqrt(T - 1))
+        if g * g != T - 1:
+            raise ValueError("token count - 1 must be a square grid")
+        self._pack()
+        ws = self._workspace(B, g * 14)
+        ws["tokens"].copy_(tokens.to(self._device(), torch.float32))
+        att = self._focal_iterations(ws, B, g, want_features).clone()
+        return (att, ws["focal_feat"].clone()) if want_features else att
+
+    # -- demo-style preprocessing ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def tokens_from_uint8(self, images_hwc_u8: torch.Tensor):
+        """uint8 [B, S, S, 3] (already at model resolution) -> backbone tokens, with ToTensor + Normalize + patchify
+        fused in one kernel (demo.py:162-166)."""
+        if images_hwc_u8.dtype != torch.uint8 or images_hwc_u8.dim() != 4 or images_hwc_u8.shape[-1] != 3:
+            raise ValueError("expected uint8 [B, S, S, 3]")
+        B, S = images_hwc_u8.shape[0], images_hwc_u8.shape[1]
+        if images_hwc_u8.shape[2] != S:
+            raise ValueError("expected square images")
+        ws = self._workspace(B, S)
+        patches = ops.preprocess_u8(images_hwc_u8.to(self._device()).contiguous(), ws["patches"])
+        return self.backbone_tokens(None, patches=patches, B=B, S=S)
+
+
+def create_model(config: dict, camera_info: Optional[dict] = None, device=None) -> CognitiveAimModel:
+    """Factory with the reference's signature (src/model.py:1534).  `config` is the whole YAML dict."""
+    cfg = dict(config)
+    if "cognitive_modules" not in cfg and "cognitive_modules" not in (cfg.get("model") or {}):
+        cfg["cognitive_modules"] = list(DEFAULT_COGNITIVE_MODULES)
+    model = CognitiveAimModel(cfg, camera_info)
+    if device is not None:
+        model = model.to(device)
+    ckpt = config.get("load_checkpoint")  # :1549 (top-level key; absent in every shipped YAML)
+    if ckpt:
+        state = torch.load(ckpt, map_location="cpu")
+        skip = ("decision_head.", "confidence_head.", "curiosity_module.", "global_aligner.", "ambient_stream.",
+                "focal_stream.", "exif_prior.", "fusion.")  # :1556-1559
+        model.load_state_dict({k: v for k, v in state.items() if not k.startswith(skip)}, strict=False)
+    return model

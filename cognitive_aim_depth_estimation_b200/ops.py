@@ -108,3 +108,64 @@ def focal_input(tokens, pe, rowscale, xin, B, N, D):
     check(_lib.load().ca_focal_input(ptr(tokens), ptr(pe), ptr(rowscale), ptr(xin), B, N, D, stream_ptr()),
           "ca_focal_input")
     return xin
+
+
+def rowstats_merge(pm, ps, weight, rmax, rinv):
+    rows, P = pm.numel() // pm.shape[-1], pm.shape[-1]
+    check(_lib.load().ca_rowstats_merge(ptr(pm), ptr(ps), ptr(weight), ptr(rmax), ptr(rinv), rows, P, stream_ptr()),
+          "ca_rowstats_merge")
+
+
+def focal_finalize(pc, cbias, attn, rs_in, rs_out, B, N, focus_strength=1.5, mode=0):
+    P = pc.shape[-1]
+    check(_lib.load().ca_focal_finalize(ptr(pc), ptr(cbias), ptr(attn), ptr(rs_in), ptr(rs_out), B, N, P,
+                                        float(focus_strength), mode, stream_ptr()), "ca_focal_finalize")
+
+
+def guided_softmax(base, mask, heat, argmax, B, N, alpha=0.7, temperature=0.05):
+    _req(base, torch.float32, "base")
+    _req(mask, torch.float32, "mask")
+    _req(argmax, torch.int32, "argmax")
+    check(_lib.load().ca_guided_softmax(ptr(base), ptr(mask), ptr(heat), ptr(argmax), B, N, alpha, temperature,
+                                        stream_ptr()), "ca_guided_softmax")
+
+
+def weighted_pool(src, src_batch_stride, row_offset, w, w2, partial, B, N, D, splits):
+    check(_lib.load().ca_weighted_pool(ptr(src), src_batch_stride, row_offset, ptr(w), ptr(w2), ptr(partial), B, N, D,
+                                       splits, stream_ptr()), "ca_weighted_pool")
+
+
+def _dp(t):
+    return None if t is None else t.data_ptr()
+
+
+def make_heads_weights(named):
+    """named: dict field -> fp32 CUDA tensor (kept alive by the caller)."""
+    w = _lib.HeadsWeights()
+    for n in _lib.HeadsWeights._names:
+        t = named[n]
+        _req(t, torch.float32, n)
+        setattr(w, n, t.data_ptr())
+    return w
+
+
+def heads(weights, *, tokens, tokens_per_img, depth, conf, B, focal_feat=None, pool_partial=None, pool_splits=0,
+          tmp_w=None, tmp_b=None, pooled_out=None, exif=None, camera_idx=None, fused_out=None):
+    import ctypes as C
+    inp = _lib.HeadsInputs(_dp(tokens), tokens_per_img, _dp(focal_feat), _dp(pool_partial), pool_splits, _dp(tmp_w),
+                           _dp(tmp_b), _dp(pooled_out), _dp(exif), _dp(camera_idx))
+    check(_lib.load().ca_heads(C.byref(weights), C.byref(inp), ptr(depth), ptr(conf), ptr(fused_out), B, stream_ptr()),
+          "ca_heads")
+
+
+def focal_value(*, tok_partial, pe_partial, splits, wv, bv, proj_w0, proj_b0, proj_w1, proj_b1, feat_out, it, n_iters,
+                B):
+    import ctypes as C
+    a = _lib.FocalValueArgs(_dp(tok_partial), _dp(pe_partial), splits, _dp(wv), _dp(bv), _dp(proj_w0), _dp(proj_b0),
+                            _dp(proj_w1), _dp(proj_b1), _dp(feat_out), it, n_iters)
+    check(_lib.load().ca_focal_value(C.byref(a), B, stream_ptr()), "ca_focal_value")
+
+
+def focal_fusion(feats, n_iters, w0, b0, w1, b1, out, B):
+    check(_lib.load().ca_focal_fusion(ptr(feats), n_iters, ptr(w0), ptr(b0), ptr(w1), ptr(b1), ptr(out), B,
+                                      stream_ptr()), "ca_focal_fusion")

@@ -81,6 +81,72 @@ int ca_layernorm(const float* x, const float* gamma, const float* beta, void* ou
 int ca_focal_input(const float* tokens, const float* pe, const float* rowscale, uint16_t* xin, int B, int N, int D,
                    void* stream);
 
+/* Focal / guidance vector stages (fp32) ---------------------------------------------------------- */
+/* Merge the per-64-column partials of CA_EPI_ROWSTATS: rmax[r] = max, rinv[r] = (weight ? weight[r] : 1) / sumexp.
+ * reference src/model.py:200 (row softmax statistics). */
+int ca_rowstats_merge(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, int rows, int P,
+                      void* stream);
+/* mode 0: FocalStream attention from CA_EPI_COLSUM partials: mean over rows + centre bias, L1 normalise, clamp 1e-8,
+ *         renormalise; optionally rs_out = rs_in * (1 + focus_strength * attn)   (src/model.py:234-282, :426).
+ * mode 1: attn = plain sum of the partials (weighted column sums of the un-guided value path). */
+int ca_focal_finalize(const float* pc, const float* cbias, float* attn, const float* rs_in, float* rs_out, int B, int N,
+                      int P, float focus_strength, int mode, void* stream);
+/* heat = softmax((alpha*mask + (1-alpha)*base)/temperature) per image; argmax = first index of the maximum.
+ * src/model.py:1404-1409. */
+int ca_guided_softmax(const float* base, const float* mask, float* heat, int32_t* argmax, int B, int N, float alpha,
+                      float temperature, void* stream);
+/* partial[b, s, :] = sum_{n in split s} w[b,n] * (w2 ? w2[b,n] : 1) * src[b*src_batch_stride + (row_offset+n)*D + :]
+ * (src/model.py:1412-1414 guided pooling; :308 weighted features).  D must be 768. */
+int ca_weighted_pool(const float* src, long long src_batch_stride, int row_offset, const float* w, const float* w2,
+                     float* partial, int B, int N, int D, int splits, void* stream);
+
+/* Heads ------------------------------------------------------------------------------------------ */
+/* All members are DEVICE pointers to fp32 row-major [out, in] weights / [out] biases of the reference modules. */
+typedef struct ca_heads_weights {
+  const float *amb_w0, *amb_b0, *amb_w1, *amb_b1, *amb_w2, *amb_b2; /* ambient_stream.mlp.{0,3,5}   src/model.py:37-44 */
+  const float* cam_emb;                                             /* exif_prior.camera_embedding [num_cameras, 64] */
+  const float *exif_w0, *exif_b0, *exif_w1, *exif_b1;               /* exif_prior.exif_encoder.{0,2} */
+  const float *exif_f0, *exif_fb0, *exif_f1, *exif_fb1;             /* exif_prior.fusion.{0,3} */
+  const float *fus_w, *fus_b;                                       /* fusion.0 [192,192] */
+  const float *dec_w, *dec_b;                                       /* decision_head.0 [1,192] */
+  const float *conf_w0, *conf_b0, *conf_w2, *conf_b2;               /* confidence_head.{0,2} */
+} ca_heads_weights;
+
+typedef struct ca_heads_inputs {
+  const float* tokens;        /* [B, tokens_per_img, 768] fp32 backbone output; row 0 of each image is CLS */
+  int tokens_per_img;
+  const float* focal_feat;    /* [B, 64] un-guided focal features, or NULL for the guided path */
+  const float* pool_partial;  /* guided: [B, pool_splits, 768] partial weighted sums of the patch tokens */
+  int pool_splits;
+  const float* tmp_w;         /* guided: per-call projection [64, 768]  (src/model.py:1421) */
+  const float* tmp_b;         /* [64] */
+  float* pooled_out;          /* optional [B, 768] (debug / tests) */
+  const float* exif;          /* [B, 3] raw focal_length, aperture, iso — or NULL (zero EXIF slot) */
+  const long long* camera_idx;/* [B] */
+} ca_heads_inputs;
+
+/* depth[B], conf[B] (and optionally fused_out[B,192]) from the backbone tokens + focal slot + EXIF.
+ * `w` and `in` are HOST pointers to the structs above.  src/model.py:1195-1230. */
+int ca_heads(const ca_heads_weights* w, const ca_heads_inputs* in, float* depth, float* conf, float* fused_out, int B,
+             void* stream);
+
+typedef struct ca_focal_value_args {
+  const float* tok_partial;  /* [B, splits, 768] partial sums of c_j * rowscale_j * tokens_j */
+  const float* pe_partial;   /* [B, splits, 768] partial sums of c_j * PE_j */
+  int splits;
+  const float *wv, *bv;              /* value_proj [768,768], [768] */
+  const float *proj_w0, *proj_b0;    /* projection.0 [256,768] */
+  const float *proj_w1, *proj_b1;    /* projection.3 [64,256] */
+  float* feat_out;                   /* [B, n_iters, 64] */
+  int iter, n_iters;
+} ca_focal_value_args;
+
+/* Un-guided focal features of one iteration: ((sum_j c_j x~_j) Wv^T + bv) -> projection (src/model.py:204,308-311). */
+int ca_focal_value(const ca_focal_value_args* a, int B, void* stream);
+/* fused[B,64] = IterativeFocalStream.fusion(cat(feats))  (src/model.py:430); feats is [B, n_iters, 64]. */
+int ca_focal_fusion(const float* feats, int n_iters, const float* w0, const float* b0, const float* w1, const float* b1,
+                    float* out, int B, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

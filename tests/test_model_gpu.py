@@ -1,0 +1,157 @@
+"""End-to-end parity of the B200 path against the CPU oracle on the same random-init weights (seed protocol of
+SURVEY.md §8c): depth abs-rel <= 1e-2, confidence / heatmap max-abs <= 1e-2, heatmap argmax cell bit-exact
+(BASELINE.json north_star tolerances, bf16 tensor-core operands with fp32 accumulation)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cogaim_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CFG = {"model": {"cognitive_modules": ["ambient_stream", "iterative_focal_stream", "exif_prior_database"]}}
+DEPTH_ABS_REL, CONF_MAX_ABS, HEAT_MAX_ABS, TOKEN_REL_FRO = 1e-2, 1e-2, 1e-2, 1.5e-2
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return orc.build_state_dict(0)
+
+
+@pytest.fixture(scope="module")
+def model(cuda_device, sd):
+    from cognitive_aim_depth_estimation_b200.model import create_model
+    m = create_model(CFG, {"num_cameras": 71}, device=cuda_device)
+    m.load_state_dict(sd)
+    return m
+
+
+@pytest.fixture(scope="module")
+def cases(sd):
+    """(S, B) -> images, exif, oracle tokens."""
+    out = {}
+    for S, B in ((224, 2), (518, 2)):
+        x = orc.synthetic_images(B, S)
+        out[(S, B)] = (x, orc.synthetic_exif(B), orc.dinov2_tokens(sd, x))
+    return out
+
+
+def _cuda_exif(ex, dev):
+    return {k: v.to(dev) for k, v in ex.items()}
+
+
+@pytest.mark.parametrize("S,B", [(224, 2), (518, 2)])
+def test_backbone_tokens(model, cases, S, B):
+    x, _, ref = cases[(S, B)]
+    tok = model.backbone_tokens(x.cuda()).cpu()
+    rel = ((tok - ref).norm() / ref.norm()).item()
+    assert torch.isfinite(tok).all()
+    assert rel < TOKEN_REL_FRO, rel
+
+
+@pytest.mark.parametrize("S,B", [(224, 2), (518, 2)])
+@pytest.mark.parametrize("instruction", orc.INSTRUCTIONS)
+def test_guided_parity(model, sd, cases, S, B, instruction):
+    x, ex, tokens = cases[(S, B)]
+    torch.manual_seed(11)
+    ref = orc.forward_with_guidance(sd, None, ex, instruction, tokens=tokens, update_history=False)
+    torch.manual_seed(11)
+    depth, conf, heat = model.forward_with_guidance(x.cuda(), _cuda_exif(ex, "cuda"), instruction, return_attention=True)
+    depth, conf, heat = depth.cpu(), conf.cpu(), heat.cpu()
+    assert depth.shape == (B, 1) and conf.shape == (B, 1) and heat.shape == ref["heatmap"].shape
+    abs_rel = ((depth - ref["depth"]).abs() / ref["depth"].abs()).max().item()
+    assert abs_rel <= DEPTH_ABS_REL, abs_rel
+    assert (conf - ref["confidence"]).abs().max().item() <= CONF_MAX_ABS
+    assert (heat - ref["heatmap"]).abs().max().item() <= HEAT_MAX_ABS
+    assert torch.allclose(heat.sum(-1), torch.ones(B), atol=1e-5)
+    ref_arg = ref["heatmap"].argmax(-1)
+    top2 = ref["heatmap"].topk(2, dim=-1).values
+    margin = ((top2[:, 0] - top2[:, 1]) / top2[:, 0]).min().item()
+    assert torch.equal(heat.argmax(-1), ref_arg), f"argmax differs (oracle top-1/top-2 relative margin {margin:.2e})"
+    assert torch.equal(model._last_argmax.cpu().long(), ref_arg)
+    assert model.get_attention_weights() is not None
+
+
+def test_focal_attention_given_oracle_tokens(model, sd, cases):
+    """The last-iteration focal attention (what decides the argmax inside the top mask ring), isolated from backbone
+    error by feeding the oracle's fp32 tokens: bf16 Q/K operands, fp32 statistics."""
+    for key in ((224, 2), (518, 2)):
+        _, _, tokens = cases[key]
+        fused_ref, ref = orc.iterative_focal_stream(sd, tokens[:, 1:], need_features=True)
+        att, feat = model.focal_attention(tokens.cuda(), want_features=True)
+        rel = ((att.cpu() - ref).abs() / ref)
+        assert rel.max().item() < 5e-2 and rel.mean().item() < 2e-3, (rel.max().item(), rel.mean().item())
+        assert torch.allclose(att.sum(-1).cpu(), torch.ones(att.shape[0]), atol=1e-5)
+        assert ((feat.cpu() - fused_ref).norm() / fused_ref.norm()).item() < 1e-2
+
+
+@pytest.mark.parametrize("with_exif", [True, False])
+def test_unguided_parity(model, sd, cases, with_exif):
+    x, ex, tokens = cases[(224, 2)]
+    ex = ex if with_exif else None
+    ref = orc.forward_unguided(sd, None, ex, tokens=tokens, update_history=False)
+    if hasattr(model, "_last_attention_weights"):
+        delattr(model, "_last_attention_weights")
+    depth, conf, att = model(x.cuda(), _cuda_exif(ex, "cuda") if ex else None, return_attention=True)
+    abs_rel = ((depth.cpu() - ref["depth"]).abs() / ref["depth"].abs()).max().item()
+    assert abs_rel <= DEPTH_ABS_REL, abs_rel
+    assert (conf.cpu() - ref["confidence"]).abs().max().item() <= CONF_MAX_ABS
+    assert (att.cpu() - ref["heatmap"]).abs().max().item() <= HEAT_MAX_ABS
+    assert torch.equal(att.cpu().argmax(-1), ref["heatmap"].argmax(-1))
+    f = model.fusion_features.cpu()
+    assert ((f - ref["fusion_features"]).norm() / ref["fusion_features"].norm()).item() < 1e-2
+    assert torch.equal(model.get_attention_weights().cpu(), att.cpu())
+
+
+def test_confidence_path_exercised(cuda_device, sd, cases):
+    """SURVEY.md §4 degeneracy guard: at seed-0 init the confidence is the constant sigmoid(2.0); flip the sign of
+    confidence_head.0.weight so that ReLU passes and the second Linear + Sigmoid actually matter."""
+    from cognitive_aim_depth_estimation_b200.model import create_model
+    sd2 = dict(sd)
+    sd2["confidence_head.0.weight"] = -sd["confidence_head.0.weight"]
+    sd2["confidence_head.0.bias"] = sd["confidence_head.0.bias"] + 0.5
+    m = create_model(CFG, {"num_cameras": 71}, device=cuda_device)
+    m.load_state_dict(sd2)
+    x, ex, tokens = cases[(224, 2)]
+    torch.manual_seed(11)
+    ref = orc.forward_with_guidance(sd2, None, ex, "left", tokens=tokens, update_history=False)
+    torch.manual_seed(11)
+    _, conf = m.forward_with_guidance(x.cuda(), _cuda_exif(ex, "cuda"), "left")
+    assert not np.allclose(ref["confidence"].numpy(), 0.8807970285, atol=1e-4)
+    assert (conf.cpu() - ref["confidence"]).abs().max().item() <= CONF_MAX_ABS
+
+
+def test_guided_without_exif_falls_back_like_reference(model, sd, cases):
+    """exif_data=None in guided mode: the reference stores the guided heatmap, fails in `fusion`, and returns the
+    un-guided forward (src/model.py:1212,1237-1240)."""
+    x, ex, tokens = cases[(224, 2)]
+    ref_u = orc.forward_unguided(sd, None, None, tokens=tokens, update_history=False)
+    torch.manual_seed(11)
+    ref_g = orc.forward_with_guidance(sd, None, ex, "top", tokens=tokens, update_history=False)
+    depth, conf, att = model.forward_with_guidance(x.cuda(), None, "top", return_attention=True)
+    assert ((depth.cpu() - ref_u["depth"]).abs() / ref_u["depth"]).max().item() <= DEPTH_ABS_REL
+    assert (att.cpu() - ref_u["heatmap"]).abs().max().item() <= HEAT_MAX_ABS
+    assert torch.equal(model.get_attention_weights().cpu().argmax(-1), ref_g["heatmap"].argmax(-1))
+
+
+def test_uint8_preprocess_path(model, cases):
+    """uint8 HWC -> fused normalise+patchify kernel == float path on the ToTensor/Normalize result (demo.py:162-166)."""
+    from cognitive_aim_depth_estimation_b200 import ops
+    u8 = torch.randint(0, 256, (2, 224, 224, 3), generator=torch.Generator().manual_seed(1235), dtype=torch.uint8)
+    mean = torch.tensor(ops.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(ops.IMAGENET_STD).view(1, 3, 1, 1)
+    xf = ((u8.permute(0, 3, 1, 2).float() / 255.0 - mean) / std).cuda()
+    t_float = model.backbone_tokens(xf).clone()
+    t_u8 = model.tokens_from_uint8(u8.cuda())
+    assert ((t_u8 - t_float).norm() / t_float.norm()).item() < 2e-3
+
+
+def test_errors_are_raised_not_swallowed(model):
+    with pytest.raises(ValueError):
+        model.forward_with_guidance(torch.zeros(1, 3, 224, 224).cuda(), {"focal_length": torch.ones(1)}, "center")
+    with pytest.raises(ValueError):
+        model(torch.zeros(1, 1, 224, 224).cuda())
+    bad = {"focal_length": torch.ones(1), "aperture": torch.ones(1), "iso": torch.ones(1),
+           "camera_idx": torch.tensor([99])}
+    with pytest.raises(ValueError):
+        model.forward_with_guidance(torch.zeros(1, 3, 224, 224).cuda(), bad, "center")
