@@ -21,6 +21,40 @@ EPI_COLSUM = 5
 EPI_F32 = 6
 
 
+class _Trace:
+    """Launch accounting: `launches` counts kernels enqueued by this module; when `events` is a list every call is
+    bracketed by CUDA events on the launching stream (bench.py reads per-kernel device time from them)."""
+    launches = 0
+    events = None
+
+
+def trace_start(with_events: bool):
+    _Trace.launches = 0
+    _Trace.events = [] if with_events else None
+
+
+def trace_stop():
+    ev, n = _Trace.events, _Trace.launches
+    _Trace.events = None
+    return n, ev
+
+
+def _begin():
+    if _Trace.events is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _end(e0, name, n_kernels, work=0.0):
+    _Trace.launches += n_kernels
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        _Trace.events.append((name, work, e0, e1))
+
+
 def _req(t, dtype, name):
     if t is None:
         return
@@ -51,10 +85,12 @@ def gemm(A, W, epilogue, out=None, *, M=None, N=None, K=None, lda=None, ldw=None
     for t, n in ((bias, "bias"), (ls, "ls"), (pos, "pos"), (part_a, "part_a"), (part_b, "part_b"),
                  (col_max, "col_max"), (col_rinv, "col_rinv")):
         _req(t, torch.float32, n)
+    e0 = _begin()
     st = lib.ca_gemm_bf16(ptr(A), ptr(W), M, N, K, lda, ldw, batch, a_batch_stride, w_batch_stride, epilogue,
                           ptr(out), ldo or 0, out_batch_stride, ptr(bias), ptr(ls), ptr(pos), patches_per_img,
                           float(scale_log2), ptr(part_a), ptr(part_b), ptr(col_max), ptr(col_rinv), stream_ptr())
     check(st, "ca_gemm_bf16")
+    _end(e0, "gemm_stats" if epilogue in (EPI_ROWSTATS, EPI_COLSUM) else "gemm", 1, 2.0 * M * N * K * batch)
     return out
 
 
@@ -69,7 +105,9 @@ def attention(qkv, out, B, T, H):
     """out[B*T, H*64] = softmax(QK^T/8)V per (image, head) (csrc/attention.cu)."""
     _req(qkv, torch.bfloat16, "qkv")
     _req(out, torch.bfloat16, "out")
+    e0 = _begin()
     check(_lib.load().ca_attention_bf16(ptr(qkv), ptr(out), B, T, H, stream_ptr()), "ca_attention_bf16")
+    _end(e0, "attention", 1, 4.0 * B * H * T * T * 64)
     return out
 
 
@@ -77,7 +115,9 @@ def patchify_f32(images, patches):
     _req(images, torch.float32, "images")
     _req(patches, torch.bfloat16, "patches")
     B, _, S, _ = images.shape
+    e0 = _begin()
     check(_lib.load().ca_patchify_f32(ptr(images), ptr(patches), B, S, stream_ptr()), "ca_patchify_f32")
+    _end(e0, "patchify", 2, float(images.numel() * 4 + patches.numel() * 2))
     return patches
 
 
@@ -88,51 +128,67 @@ def preprocess_u8(images_hwc, patches, mean=IMAGENET_MEAN, std=IMAGENET_STD):
     B, S = images_hwc.shape[0], images_hwc.shape[1]
     m = (C.c_float * 3)(*mean)
     s = (C.c_float * 3)(*std)
+    e0 = _begin()
     check(_lib.load().ca_preprocess_u8(ptr(images_hwc), ptr(patches), B, S, m, s, stream_ptr()), "ca_preprocess_u8")
+    _end(e0, "preprocess_u8", 2, float(images_hwc.numel() + patches.numel() * 2))
     return patches
 
 
 def cls_rows(x, cls, pos, B, T, D):
+    e0 = _begin()
     check(_lib.load().ca_cls_rows(ptr(x), ptr(cls), ptr(pos), B, T, D, stream_ptr()), "ca_cls_rows")
+    _end(e0, "small", 1)
 
 
 def layernorm(x, gamma, beta, out, eps=1e-6):
     _req(x, torch.float32, "x")
     rows, D = x.numel() // x.shape[-1], x.shape[-1]
+    e0 = _begin()
     check(_lib.load().ca_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), int(out.dtype == torch.bfloat16), rows, D,
                                    eps, stream_ptr()), "ca_layernorm")
+    _end(e0, "layernorm", 1, float(rows * D * (4 + out.element_size())))
     return out
 
 
 def focal_input(tokens, pe, rowscale, xin, B, N, D):
+    e0 = _begin()
     check(_lib.load().ca_focal_input(ptr(tokens), ptr(pe), ptr(rowscale), ptr(xin), B, N, D, stream_ptr()),
           "ca_focal_input")
+    _end(e0, "focal_input", 1, float(B * N * D * 6))
     return xin
 
 
 def rowstats_merge(pm, ps, weight, rmax, rinv):
     rows, P = pm.numel() // pm.shape[-1], pm.shape[-1]
+    e0 = _begin()
     check(_lib.load().ca_rowstats_merge(ptr(pm), ptr(ps), ptr(weight), ptr(rmax), ptr(rinv), rows, P, stream_ptr()),
           "ca_rowstats_merge")
+    _end(e0, "small", 1)
 
 
 def focal_finalize(pc, cbias, attn, rs_in, rs_out, B, N, focus_strength=1.5, mode=0):
     P = pc.shape[-1]
+    e0 = _begin()
     check(_lib.load().ca_focal_finalize(ptr(pc), ptr(cbias), ptr(attn), ptr(rs_in), ptr(rs_out), B, N, P,
                                         float(focus_strength), mode, stream_ptr()), "ca_focal_finalize")
+    _end(e0, "small", 1)
 
 
 def guided_softmax(base, mask, heat, argmax, B, N, alpha=0.7, temperature=0.05):
     _req(base, torch.float32, "base")
     _req(mask, torch.float32, "mask")
     _req(argmax, torch.int32, "argmax")
+    e0 = _begin()
     check(_lib.load().ca_guided_softmax(ptr(base), ptr(mask), ptr(heat), ptr(argmax), B, N, alpha, temperature,
                                         stream_ptr()), "ca_guided_softmax")
+    _end(e0, "small", 1)
 
 
 def weighted_pool(src, src_batch_stride, row_offset, w, w2, partial, B, N, D, splits):
+    e0 = _begin()
     check(_lib.load().ca_weighted_pool(ptr(src), src_batch_stride, row_offset, ptr(w), ptr(w2), ptr(partial), B, N, D,
                                        splits, stream_ptr()), "ca_weighted_pool")
+    _end(e0, "pool", 1, float(B * N * D * 4))
 
 
 def _dp(t):
@@ -154,8 +210,10 @@ def heads(weights, *, tokens, tokens_per_img, depth, conf, B, focal_feat=None, p
     import ctypes as C
     inp = _lib.HeadsInputs(_dp(tokens), tokens_per_img, _dp(focal_feat), _dp(pool_partial), pool_splits, _dp(tmp_w),
                            _dp(tmp_b), _dp(pooled_out), _dp(exif), _dp(camera_idx))
+    e0 = _begin()
     check(_lib.load().ca_heads(C.byref(weights), C.byref(inp), ptr(depth), ptr(conf), ptr(fused_out), B, stream_ptr()),
           "ca_heads")
+    _end(e0, "heads", 1)
 
 
 def focal_value(*, tok_partial, pe_partial, splits, wv, bv, proj_w0, proj_b0, proj_w1, proj_b1, feat_out, it, n_iters,
@@ -163,9 +221,13 @@ def focal_value(*, tok_partial, pe_partial, splits, wv, bv, proj_w0, proj_b0, pr
     import ctypes as C
     a = _lib.FocalValueArgs(_dp(tok_partial), _dp(pe_partial), splits, _dp(wv), _dp(bv), _dp(proj_w0), _dp(proj_b0),
                             _dp(proj_w1), _dp(proj_b1), _dp(feat_out), it, n_iters)
+    e0 = _begin()
     check(_lib.load().ca_focal_value(C.byref(a), B, stream_ptr()), "ca_focal_value")
+    _end(e0, "heads", 1)
 
 
 def focal_fusion(feats, n_iters, w0, b0, w1, b1, out, B):
+    e0 = _begin()
     check(_lib.load().ca_focal_fusion(ptr(feats), n_iters, ptr(w0), ptr(b0), ptr(w1), ptr(b1), ptr(out), B,
                                       stream_ptr()), "ca_focal_fusion")
+    _end(e0, "heads", 1)
