@@ -46,6 +46,69 @@ struct AttnArgs {
   int ldo;
 };
 
+// One softmax step for one query row (thread) over a 128-key S tile held in TMEM:
+//   pass 1: row max of the raw accumulators (4 independent chains, no per-element scaling)
+//   pass 2: P = exp2(s*scale - max) -> bf16 -> 128B-swizzled smem (A operand of the PV MMA), fp32 row sum
+// TMEM loads are software-pipelined (chunk c+1 is in flight while chunk c is processed).  kMasked is only
+// instantiated for the ragged last tile, so the steady-state path carries no predicates.
+template <bool kMasked>
+__device__ __forceinline__ float softmax_tile(uint32_t t_s, uint8_t* p_row, int r, int valid, float scale_log2,
+                                              float m_run, float& sum_out) {
+  uint32_t v[2][32];
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  tmem_ld32(t_s, v[0]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tmem_ld_wait();
+    if (c < 3) tmem_ld32(t_s + (c + 1) * 32, v[(c + 1) & 1]);
+    else tmem_ld32(t_s, v[0]);  // chunk 0 again for pass 2
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float x0 = __uint_as_float(v[c & 1][i + 0]), x1 = __uint_as_float(v[c & 1][i + 1]);
+      float x2 = __uint_as_float(v[c & 1][i + 2]), x3 = __uint_as_float(v[c & 1][i + 3]);
+      if (kMasked) {
+        x0 = (c * 32 + i + 0 < valid) ? x0 : -INFINITY;
+        x1 = (c * 32 + i + 1 < valid) ? x1 : -INFINITY;
+        x2 = (c * 32 + i + 2 < valid) ? x2 : -INFINITY;
+        x3 = (c * 32 + i + 3 < valid) ? x3 : -INFINITY;
+      }
+      m0 = fmaxf(m0, x0);
+      m1 = fmaxf(m1, x1);
+      m2 = fmaxf(m2, x2);
+      m3 = fmaxf(m3, x3);
+    }
+  }
+  const float mx = fmaxf(m_run, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale_log2);  // scale_log2 > 0
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tmem_ld_wait();
+    if (c < 3) tmem_ld32(t_s + (c + 1) * 32, v[(c + 1) & 1]);
+    uint8_t* chunk_base = p_row + (c >> 1) * kTileBytes;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float e[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        e[i] = fast_exp2(fmaf(__uint_as_float(v[c & 1][8 * t + i]), scale_log2, -mx));
+        if (kMasked) e[i] = (c * 32 + 8 * t + i < valid) ? e[i] : 0.f;
+      }
+      s0 += e[0] + e[4];
+      s1 += e[1] + e[5];
+      s2 += e[2] + e[6];
+      s3 += e[3] + e[7];
+      uint4 w;
+      w.x = pack_bf16x2(e[0], e[1]);
+      w.y = pack_bf16x2(e[2], e[3]);
+      w.z = pack_bf16x2(e[4], e[5]);
+      w.w = pack_bf16x2(e[6], e[7]);
+      *reinterpret_cast<uint4*>(chunk_base + sw128_offset(r, (c & 1) * 4 + t)) = w;
+    }
+  }
+  sum_out = (s0 + s1) + (s2 + s3);
+  return mx;
+}
+
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -142,46 +205,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArg
     float m_run = -INFINITY;
     float l_run = 0.f;
     for (int j = 0; j < p.n_kv; ++j) {
-      const int valid = min(kTileK, p.T - j * kTileK);  // keys of this tile that exist
+      const int valid = p.T - j * kTileK;  // >= 128 on every tile but the last
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // ---- pass 1: running max (base-2 logits) ----
-      float mx = m_run;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]) * p.scale_log2);
+      float mx, sum;
+      if (valid >= kTileK) {
+        mx = softmax_tile<false>(t_s, p_row, r, kTileK, p.scale_log2, m_run, sum);
+      } else {
+        mx = softmax_tile<true>(t_s, p_row, r, valid, p.scale_log2, m_run, sum);
       }
       const float alpha = fast_exp2(m_run - mx);  // 0 on the first tile (m_run = -inf)
-      // ---- pass 2: P = exp2(s - max) -> bf16 -> swizzled smem ; row sum ----
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c * 32, v);
-        tmem_ld_wait();
-        float e[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -mx));
-          e[i] = (c * 32 + i < valid) ? x : 0.f;
-          sum += e[i];
-        }
-        uint8_t* chunk_base = p_row + (c >> 1) * kTileBytes;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          uint4 w;
-          w.x = pack_bf16x2(e[8 * t + 0], e[8 * t + 1]);
-          w.y = pack_bf16x2(e[8 * t + 2], e[8 * t + 3]);
-          w.z = pack_bf16x2(e[8 * t + 4], e[8 * t + 5]);
-          w.w = pack_bf16x2(e[8 * t + 6], e[8 * t + 7]);
-          *reinterpret_cast<uint4*>(chunk_base + sw128_offset(r, (c & 1) * 4 + t)) = w;
-        }
-      }
       l_run = l_run * alpha + sum;
       m_run = mx;
       // ---- rescale the O accumulator when any row of this warp moved its max (warp-uniform branch) ----

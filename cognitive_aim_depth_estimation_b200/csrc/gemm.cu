@@ -27,6 +27,10 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // one 128-byte swizzle atom of bf16
 constexpr int kNumEpiWarps = 8;
 constexpr int kGemmThreads = (2 + kNumEpiWarps) * 32;
+// Epilogue staging: one 32-row x 64-byte output chunk per warp, rows padded to 80 bytes (20 words) so that both the
+// thread-per-row 16-byte writes and the 8-rows-x-4-segments 16-byte reads are bank-conflict free.
+constexpr int kEpiRowBytes = 80;
+constexpr int kEpiStageBytes = 32 * kEpiRowBytes;
 
 template <int BN>
 struct GemmCfg {
@@ -35,7 +39,8 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // 512 or 256: power of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = kNumEpiWarps * kEpiStageBytes;  // epilogue transposition buffers
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmKernelArgs {
@@ -62,7 +67,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // One epilogue warp: rows [32*q, 32*q+32) of the tile (q = warp_id % 4), columns [col0, col0 + BN/2).
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, uint32_t tmem_acc, int b, int mt, int nt,
-                                              int quad, int half) {
+                                              int quad, int half, uint8_t* stage) {
   constexpr int kSpan = BN / 2;
   const int lane = lane_id();
   const int row = mt * BM + quad * 32 + lane;           // row inside batch b
@@ -126,86 +131,108 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, uint32_t 
     }
     return;
   } else {
-    // Dense epilogues: 32 columns at a time, one row per thread.
-    size_t orow;
-    if constexpr (EPI == EPI_PATCH_F32) {
-      const int img = row / p.patches_per_img;
-      const int pidx = row - img * p.patches_per_img;
-      orow = static_cast<size_t>(img) * (p.patches_per_img + 1) + 1 + pidx;
-    } else {
-      orow = static_cast<size_t>(row);
-    }
+    // Dense epilogues.  TMEM hands each thread one accumulator ROW; global memory wants each warp instruction to
+    // cover whole 32-byte sectors of a few rows.  So every 64-byte-per-row output chunk (32 bf16 or 16 fp32 columns)
+    // is finished per row in registers (bias, GELU), transposed through a padded smem buffer, and then read /
+    // modified / written with lanes laid out as 8 rows x 4 x 16 B: every global access moves full sectors.
+    const int lr = lane & 7;   // row within a group of 8
+    const int seg = lane >> 3; // 16-byte segment of the 64-byte chunk row
+    if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16) {
 #pragma unroll 1
-    for (int c = 0; c < kSpan; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(taddr + c, v);
-      tmem_ld_wait();
-      const int col = col_base + c;
-      // N is a multiple of 32 for the dense epilogues (checked on the host), so `col < N` is warp-uniform;
-      // `row_ok` is per lane, hence no `continue` here: the next tcgen05.ld needs a converged warp.
-      if (row_ok && col < p.N) {
-      float acc[32];
+      for (int c = 0; c < kSpan; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        const int col = col_base + c;
+        if (col < p.N) {  // warp-uniform (N % 32 == 0 is checked on the host)
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-      if constexpr (EPI != EPI_F32) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+          for (int j = 0; j < 4; ++j) {
+            float a[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = __ldg(b4 + j);
-          acc[4 * j + 0] += t.x;
-          acc[4 * j + 1] += t.y;
-          acc[4 * j + 2] += t.z;
-          acc[4 * j + 3] += t.w;
-        }
-      }
-      if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16) {
-        if constexpr (EPI == EPI_GELU_BF16) {
+            for (int h = 0; h < 2; ++h) {
+              const float4 t = __ldg(b4 + 2 * j + h);
+              a[4 * h + 0] = __uint_as_float(v[8 * j + 4 * h + 0]) + t.x;
+              a[4 * h + 1] = __uint_as_float(v[8 * j + 4 * h + 1]) + t.y;
+              a[4 * h + 2] = __uint_as_float(v[8 * j + 4 * h + 2]) + t.z;
+              a[4 * h + 3] = __uint_as_float(v[8 * j + 4 * h + 3]) + t.w;
+            }
+            if constexpr (EPI == EPI_GELU_BF16) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
-        }
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride +
-                           orow * p.ldo + col;
-        uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 t;
-          t.x = pack_bf16x2(acc[8 * j + 0], acc[8 * j + 1]);
-          t.y = pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]);
-          t.z = pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]);
-          t.w = pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]);
-          o4[j] = t;
-        }
-      } else {
-        float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride + orow * p.ldo + col;
-        float4* o4 = reinterpret_cast<float4*>(o);
-        if constexpr (EPI == EPI_RESID_F32) {
-          const float4* l4 = reinterpret_cast<const float4*>(p.ls + col);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 l = __ldg(l4 + j);
-            float4 x = o4[j];
-            x.x = fmaf(l.x, acc[4 * j + 0], x.x);
-            x.y = fmaf(l.y, acc[4 * j + 1], x.y);
-            x.z = fmaf(l.z, acc[4 * j + 2], x.z);
-            x.w = fmaf(l.w, acc[4 * j + 3], x.w);
-            o4[j] = x;
+              for (int i = 0; i < 8; ++i) a[i] = gelu_erf(a[i]);
+            }
+            uint4 w;
+            w.x = pack_bf16x2(a[0], a[1]);
+            w.y = pack_bf16x2(a[2], a[3]);
+            w.z = pack_bf16x2(a[4], a[5]);
+            w.w = pack_bf16x2(a[6], a[7]);
+            *reinterpret_cast<uint4*>(stage + lane * kEpiRowBytes + 16 * j) = w;
           }
-        } else if constexpr (EPI == EPI_PATCH_F32) {
-          const int pidx = row % p.patches_per_img;
-          const float4* q4 = reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + pidx) * p.N + col);
+          __syncwarp();
+          __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride + col;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 q = __ldg(q4 + j);
-            o4[j] = make_float4(acc[4 * j + 0] + q.x, acc[4 * j + 1] + q.y, acc[4 * j + 2] + q.z, acc[4 * j + 3] + q.w);
+          for (int i = 0; i < 4; ++i) {
+            const int rr = lr + 8 * i;
+            const int grow = mt * BM + quad * 32 + rr;
+            const uint4 w = *reinterpret_cast<const uint4*>(stage + rr * kEpiRowBytes + 16 * seg);
+            if (grow < p.M) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(grow) * p.ldo + seg * 8) = w;
           }
-        } else {  // EPI_F32
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o4[j] = make_float4(acc[4 * j + 0], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          __syncwarp();
         }
       }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < kSpan; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        const int col = col_base + c;
+        if (col < p.N) {  // warp-uniform (N % 32 == 0)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 a = make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
+                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            if constexpr (EPI != EPI_F32) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+              a.x += t.x;
+              a.y += t.y;
+              a.z += t.z;
+              a.w += t.w;
+            }
+            *reinterpret_cast<float4*>(stage + lane * kEpiRowBytes + 16 * j) = a;
+          }
+          __syncwarp();
+          float4 l4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if constexpr (EPI == EPI_RESID_F32) l4 = __ldg(reinterpret_cast<const float4*>(p.ls + col) + seg);
+          float* obase = reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride + col + seg * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = lr + 8 * i;
+            const int grow = mt * BM + quad * 32 + rr;
+            const float4 a = *reinterpret_cast<const float4*>(stage + rr * kEpiRowBytes + 16 * seg);
+            if (grow < p.M) {
+              if constexpr (EPI == EPI_RESID_F32) {
+                float4* o = reinterpret_cast<float4*>(obase + static_cast<size_t>(grow) * p.ldo);
+                float4 x = *o;
+                x.x = fmaf(l4.x, a.x, x.x);
+                x.y = fmaf(l4.y, a.y, x.y);
+                x.z = fmaf(l4.z, a.z, x.z);
+                x.w = fmaf(l4.w, a.w, x.w);
+                *o = x;
+              } else if constexpr (EPI == EPI_PATCH_F32) {
+                const int img = grow / p.patches_per_img;
+                const int pidx = grow - img * p.patches_per_img;
+                const size_t orow = static_cast<size_t>(img) * (p.patches_per_img + 1) + 1 + pidx;
+                const float4 q = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + pidx) * p.N + col) + seg);
+                *reinterpret_cast<float4*>(obase + orow * p.ldo) = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+              } else {  // EPI_F32
+                *reinterpret_cast<float4*>(obase + static_cast<size_t>(grow) * p.ldo) = a;
+              }
+            }
+          }
+          __syncwarp();
+        }
       }
-      __syncwarp();
     }
   }
 }
@@ -220,7 +247,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_stage = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;                        // [kStages] TMA -> MMA
   uint64_t* empty_bar = bars + Cfg::kStages;        // [kStages] MMA -> TMA
   uint64_t* acc_full = bars + 2 * Cfg::kStages;     // [2] MMA -> epilogue
@@ -317,7 +345,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int b = rest / p.m_tiles;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN, EPI>(p, tmem_base + static_cast<uint32_t>(acc * BN), b, mt, nt, quad, half);
+      epilogue_tile<BN, EPI>(p, tmem_base + static_cast<uint32_t>(acc * BN), b, mt, nt, quad, half,
+                             smem_stage + e * kEpiStageBytes);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
