@@ -19,6 +19,8 @@
 #include "gemm.cuh"
 #include "host.h"
 
+#include <stdlib.h>
+
 namespace ca {
 
 namespace {
@@ -27,10 +29,12 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // one 128-byte swizzle atom of bf16
 constexpr int kNumEpiWarps = 8;
 constexpr int kGemmThreads = (2 + kNumEpiWarps) * 32;
-// Epilogue staging: one 32-row x 64-byte output chunk per warp, rows padded to 80 bytes (20 words) so that both the
-// thread-per-row 16-byte writes and the 8-rows-x-4-segments 16-byte reads are bank-conflict free.
-constexpr int kEpiRowBytes = 80;
-constexpr int kEpiStageBytes = 32 * kEpiRowBytes;
+// Epilogue staging: one 32-row x 128-byte output chunk per warp (32 fp32 or 64 bf16 columns).  The 16-byte piece j of
+// row r lives at r*128 + ((j ^ (r & 7)) << 4): the thread-per-row writes (fixed j, 8 consecutive rows per quarter
+// warp) and the row-contiguous reads (fixed row, 8 pieces per quarter warp) are both bank-conflict free, and every
+// global access of the read side covers whole 128-byte lines (4 rows x 128 B per warp instruction).
+constexpr int kEpiStageBytes = 32 * 128;
+__device__ __forceinline__ uint32_t epi_off(int r, int piece) { return r * 128 + ((piece ^ (r & 7)) << 4); }
 
 template <int BN>
 struct GemmCfg {
@@ -60,14 +64,40 @@ struct GemmKernelArgs {
   const float* col_max;
   const float* col_rinv;
   int partials;
+  int dbg;  // CA_GEMM_DEBUG experiments (bit 0: skip B loads, bit 1: skip A loads) — results are then garbage
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)) = relu(x) - |x| * erfc(|x| / sqrt 2) / 2, with erfc from Abramowitz &
+// Stegun 7.1.26 (|abs err| <= 1.5e-7 on erf, 4e-7 on GELU: three orders below the bf16 rounding of the output).
+// 2 MUFU (rcp, ex2) + 11 FMA-pipe ops, branch-free; the negative tail is evaluated directly (no cancellation).
+// w = |x| * sqrt(log2(e) / 2) so that exp(-z^2) = 2^(-w^2); the 1/2 is folded into the polynomial coefficients.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float ax = fabsf(x);
+  const float w = ax * 0.84932180028801904f;
+  const float t = __fdividef(1.0f, fmaf(0.27273784f, w, 1.0f));  // 1 / (1 + 0.3275911 z)
+  float poly = fmaf(0.5307027145f, t, -0.7265760135f);
+  poly = fmaf(poly, t, 0.7107068705f);
+  poly = fmaf(poly, t, -0.142248368f);
+  poly = fmaf(poly, t, 0.127414796f);
+  const float half_erfc = poly * t * fast_exp2(-w * w);
+  return fmaf(-ax, half_erfc, fmaxf(x, 0.f));
+}
+
+// Residual loads of one 32-column chunk for this lane's (8 rows x 16 B) slots; rows past M are skipped.
+__device__ __forceinline__ void resid_load_chunk(const GemmKernelArgs& p, const float* xchunk, int mt, int quad,
+                                                 int lrow, float4 (&dst)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int grow = mt * BM + quad * 32 + lrow + 4 * i;
+    if (grow < p.M && !(p.dbg & 4)) dst[i] = *reinterpret_cast<const float4*>(xchunk + static_cast<size_t>(grow) * p.ldo);
+  }
+}
 
 // One epilogue warp: rows [32*q, 32*q+32) of the tile (q = warp_id % 4), columns [col0, col0 + BN/2).
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, uint32_t tmem_acc, int b, int mt, int nt,
-                                              int quad, int half, uint8_t* stage) {
+                                              int quad, int half, uint8_t* stage,
+                                              float4 (&xr)[2][8]) {
   constexpr int kSpan = BN / 2;
   const int lane = lane_id();
   const int row = mt * BM + quad * 32 + lane;           // row inside batch b
@@ -135,61 +165,106 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, uint32_t 
     // cover whole 32-byte sectors of a few rows.  So every 64-byte-per-row output chunk (32 bf16 or 16 fp32 columns)
     // is finished per row in registers (bias, GELU), transposed through a padded smem buffer, and then read /
     // modified / written with lanes laid out as 8 rows x 4 x 16 B: every global access moves full sectors.
-    const int lr = lane & 7;   // row within a group of 8
-    const int seg = lane >> 3; // 16-byte segment of the 64-byte chunk row
+    const int lrow = lane >> 3;  // row within a group of 4 (8 passes cover the warp's 32 rows)
+    const int seg = lane & 7;    // 16-byte piece of the 128-byte chunk row
     if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16) {
+#pragma unroll 1
+      for (int c = 0; c < kSpan; c += 64) {
+        const int col = col_base + c;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c + 32 * hh, v);
+          tmem_ld_wait();
+          if (col < p.N) {  // warp-uniform (N % 64 == 0 is checked on the host)
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col + 32 * hh);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a[8];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float4 t = __ldg(b4 + 2 * j + h);
+                a[4 * h + 0] = __uint_as_float(v[8 * j + 4 * h + 0]) + t.x;
+                a[4 * h + 1] = __uint_as_float(v[8 * j + 4 * h + 1]) + t.y;
+                a[4 * h + 2] = __uint_as_float(v[8 * j + 4 * h + 2]) + t.z;
+                a[4 * h + 3] = __uint_as_float(v[8 * j + 4 * h + 3]) + t.w;
+              }
+              if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = gelu_erf(a[i]);
+              }
+              uint4 w;
+              w.x = pack_bf16x2(a[0], a[1]);
+              w.y = pack_bf16x2(a[2], a[3]);
+              w.z = pack_bf16x2(a[4], a[5]);
+              w.w = pack_bf16x2(a[6], a[7]);
+              *reinterpret_cast<uint4*>(stage + epi_off(lane, 4 * hh + j)) = w;
+            }
+          }
+        }
+        if (col < p.N) {
+          __syncwarp();
+          __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride +
+                                 col + seg * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = lrow + 4 * i;
+            const int grow = mt * BM + quad * 32 + rr;
+            const uint4 w = *reinterpret_cast<const uint4*>(stage + epi_off(rr, seg));
+            if (grow < p.M) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(grow) * p.ldo) = w;
+          }
+          __syncwarp();
+        }
+      }
+    } else if constexpr (EPI == EPI_RESID_F32) {
+      // x += ls * (acc + bias), in place.  The residual reads are the only long-latency operation of this epilogue
+      // (x does not fit L2 between layers), so they are software-pipelined one 32-column chunk ahead, and chunk 0 was
+      // issued by resid_load_chunk() BEFORE the wait on the accumulator, i.e. it overlaps the tile's own MMAs.
+      float* xbase = reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride + col_base + seg * 4;
+      constexpr int kChunks = kSpan / 32;
+#pragma unroll
+      for (int g = 0; g < kChunks; ++g) {
+        if (g + 1 < kChunks) resid_load_chunk(p, xbase + (g + 1) * 32, mt, quad, lrow, xr[(g + 1) & 1]);
+        const int c = g * 32;
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        const int col = col_base + c;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+          *reinterpret_cast<float4*>(stage + epi_off(lane, j)) =
+              make_float4(__uint_as_float(v[4 * j + 0]) + t.x, __uint_as_float(v[4 * j + 1]) + t.y,
+                          __uint_as_float(v[4 * j + 2]) + t.z, __uint_as_float(v[4 * j + 3]) + t.w);
+        }
+        __syncwarp();
+        const float4 l4 = __ldg(reinterpret_cast<const float4*>(p.ls + col) + seg);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = lrow + 4 * i;
+          const int grow = mt * BM + quad * 32 + rr;
+          const float4 a = *reinterpret_cast<const float4*>(stage + epi_off(rr, seg));
+          if (grow < p.M && !(p.dbg & 8)) {
+            float4 x = xr[g & 1][i];
+            x.x = fmaf(l4.x, a.x, x.x);
+            x.y = fmaf(l4.y, a.y, x.y);
+            x.z = fmaf(l4.z, a.z, x.z);
+            x.w = fmaf(l4.w, a.w, x.w);
+            *reinterpret_cast<float4*>(xbase + static_cast<size_t>(grow) * p.ldo + c) = x;
+          }
+        }
+        __syncwarp();
+      }
+    } else {
 #pragma unroll 1
       for (int c = 0; c < kSpan; c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
         const int col = col_base + c;
-        if (col < p.N) {  // warp-uniform (N % 32 == 0 is checked on the host)
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float a[8];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float4 t = __ldg(b4 + 2 * j + h);
-              a[4 * h + 0] = __uint_as_float(v[8 * j + 4 * h + 0]) + t.x;
-              a[4 * h + 1] = __uint_as_float(v[8 * j + 4 * h + 1]) + t.y;
-              a[4 * h + 2] = __uint_as_float(v[8 * j + 4 * h + 2]) + t.z;
-              a[4 * h + 3] = __uint_as_float(v[8 * j + 4 * h + 3]) + t.w;
-            }
-            if constexpr (EPI == EPI_GELU_BF16) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) a[i] = gelu_erf(a[i]);
-            }
-            uint4 w;
-            w.x = pack_bf16x2(a[0], a[1]);
-            w.y = pack_bf16x2(a[2], a[3]);
-            w.z = pack_bf16x2(a[4], a[5]);
-            w.w = pack_bf16x2(a[6], a[7]);
-            *reinterpret_cast<uint4*>(stage + lane * kEpiRowBytes + 16 * j) = w;
-          }
-          __syncwarp();
-          __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride + col;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = lr + 8 * i;
-            const int grow = mt * BM + quad * 32 + rr;
-            const uint4 w = *reinterpret_cast<const uint4*>(stage + rr * kEpiRowBytes + 16 * seg);
-            if (grow < p.M) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(grow) * p.ldo + seg * 8) = w;
-          }
-          __syncwarp();
-        }
-      }
-    } else {
-#pragma unroll 1
-      for (int c = 0; c < kSpan; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c, v);
-        tmem_ld_wait();
-        const int col = col_base + c;
         if (col < p.N) {  // warp-uniform (N % 32 == 0)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 8; ++j) {
             float4 a = make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
             if constexpr (EPI != EPI_F32) {
@@ -199,27 +274,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, uint32_t 
               a.z += t.z;
               a.w += t.w;
             }
-            *reinterpret_cast<float4*>(stage + lane * kEpiRowBytes + 16 * j) = a;
+            *reinterpret_cast<float4*>(stage + epi_off(lane, j)) = a;
           }
           __syncwarp();
-          float4 l4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if constexpr (EPI == EPI_RESID_F32) l4 = __ldg(reinterpret_cast<const float4*>(p.ls + col) + seg);
           float* obase = reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride + col + seg * 4;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = lr + 8 * i;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = lrow + 4 * i;
             const int grow = mt * BM + quad * 32 + rr;
-            const float4 a = *reinterpret_cast<const float4*>(stage + rr * kEpiRowBytes + 16 * seg);
+            const float4 a = *reinterpret_cast<const float4*>(stage + epi_off(rr, seg));
             if (grow < p.M) {
-              if constexpr (EPI == EPI_RESID_F32) {
-                float4* o = reinterpret_cast<float4*>(obase + static_cast<size_t>(grow) * p.ldo);
-                float4 x = *o;
-                x.x = fmaf(l4.x, a.x, x.x);
-                x.y = fmaf(l4.y, a.y, x.y);
-                x.z = fmaf(l4.z, a.z, x.z);
-                x.w = fmaf(l4.w, a.w, x.w);
-                *o = x;
-              } else if constexpr (EPI == EPI_PATCH_F32) {
+              if constexpr (EPI == EPI_PATCH_F32) {
                 const int img = grow / p.patches_per_img;
                 const int pidx = grow - img * p.patches_per_img;
                 const size_t orow = static_cast<size_t>(img) * (p.patches_per_img + 1) + 1 + pidx;
@@ -238,7 +303,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, uint32_t 
 }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)  // 10 warps -> 3 warps on two SMSPs -> 168 registers per thread
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const GemmKernelArgs p) {
   using Cfg = GemmCfg<BN>;
@@ -289,10 +354,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int b = rest / p.m_tiles;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_3d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK, mt * BM, b);
-          tma_load_3d(smem_b + stage * Cfg::kBBytes, &tmap_w, &full_bar[stage], kb * BK, nt * BN,
-                      p.w_batched ? b : 0);
+          const bool la = !(p.dbg & 2) || kb == 0, lb = !(p.dbg & 1) || kb == 0;
+          mbar_arrive_expect_tx(&full_bar[stage], (la ? Cfg::kABytes : 0) + (lb ? Cfg::kBBytes : 0));
+          if (la) tma_load_3d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK, mt * BM, b);
+          if (lb)
+            tma_load_3d(smem_b + stage * Cfg::kBBytes, &tmap_w, &full_bar[stage], kb * BK, nt * BN,
+                        p.w_batched ? b : 0);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1u;
@@ -343,10 +410,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int rest = tile / p.n_tiles;
       const int mt = rest % p.m_tiles;
       const int b = rest / p.m_tiles;
+      float4 xr[2][8];
+      if constexpr (EPI == EPI_RESID_F32) {  // first residual chunk: issued before the accumulator is ready
+        const float* xbase = reinterpret_cast<const float*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride +
+                             nt * BN + half * (BN / 2) + (lane & 7) * 4;
+        resid_load_chunk(p, xbase, mt, quad, lane >> 3, xr[0]);
+      }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       epilogue_tile<BN, EPI>(p, tmem_base + static_cast<uint32_t>(acc * BN), b, mt, nt, quad, half,
-                             smem_stage + e * kEpiStageBytes);
+                             smem_stage + e * kEpiStageBytes, xr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -389,11 +462,14 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   const int bn = stats ? 128 : 256;
   if (!stats) {
     CA_REQUIRE(a.N % 32 == 0, "gemm: N must be a multiple of 32 for the dense epilogues");
+    CA_REQUIRE((a.epilogue != EPI_BIAS_BF16 && a.epilogue != EPI_GELU_BF16) || a.N % 64 == 0,
+               "gemm: the bf16 epilogues need N % 64 == 0");
     CA_REQUIRE(a.out != nullptr, "gemm: null output");
     CA_REQUIRE(a.epilogue == EPI_F32 || a.bias != nullptr, "gemm: null bias");
     const int vec = (a.epilogue == EPI_BIAS_BF16 || a.epilogue == EPI_GELU_BF16) ? 8 : 4;
     CA_REQUIRE(a.ldo % vec == 0, "gemm: ldo must keep rows 16-byte aligned");
     CA_REQUIRE(a.epilogue != EPI_RESID_F32 || a.ls != nullptr, "gemm: null LayerScale");
+    CA_REQUIRE(a.epilogue != EPI_RESID_F32 || a.N % 256 == 0, "gemm: the residual epilogue needs N % 256 == 0");
     CA_REQUIRE(a.epilogue != EPI_PATCH_F32 || (a.pos != nullptr && a.patches_per_img > 0), "gemm: null pos-embed");
   } else {
     CA_REQUIRE(a.part_a != nullptr, "gemm: null partial buffer");
@@ -431,6 +507,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   ka.col_max = a.col_max;
   ka.col_rinv = a.col_rinv;
   ka.partials = gemm_stats_partials(a.N);
+  static const int dbg = getenv("CA_GEMM_DEBUG") ? atoi(getenv("CA_GEMM_DEBUG")) : 0;
+  ka.dbg = dbg;
 
   switch (a.epilogue) {
     case EPI_BIAS_BF16: return launch_inst<256, EPI_BIAS_BF16>(ta, tw, ka, stream);
