@@ -32,6 +32,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ uint32_t warp_id() { return threadIdx.x >> 5; }
 
+// One elected lane of a fully converged warp (the compiler then issues the following uniform-datapath
+// instructions — UTCHMMA, UTMALDG, UTCBAR — once, without wrapping each of them in an ELECT loop).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
