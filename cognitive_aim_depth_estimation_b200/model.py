@@ -155,6 +155,7 @@ class CognitiveAimModel(nn.Module):
         self._tables: Dict = {}   # per-grid tables (pos-embed, PE, centre bias, masks)
         self._ws: Dict = {}       # workspaces keyed by (B, S)
         self.validate_inputs = True
+        self.rng_replay_batch = None  # sharded runs: replay the reference's RNG draws at the GLOBAL batch size
         self.eval()
 
     # -- nn.Module protocol -----------------------------------------------------------------------------
@@ -417,10 +418,11 @@ class CognitiveAimModel(nn.Module):
             raise ValueError("camera_idx out of range")  # (one tiny D2H sync; disable for CUDA-graph capture)
         return cont, cam
 
-    @staticmethod
-    def _replay_reference_rng(B: int):
+    def _replay_reference_rng(self, B: int):
         """CuriosityModule draws randn(B,192) then randn(B,768) on the global CPU generator in eval
-        (src/model.py:609,744) before the per-call projection is initialised (:1421)."""
+        (src/model.py:609,744) before the per-call projection is initialised (:1421).  A batch-sharded run sets
+        `rng_replay_batch` to the global batch so every shard sees the projection of the un-sharded call."""
+        B = self.rng_replay_batch or B
         torch.randn(B, 192)
         torch.randn(B, 768)
 
