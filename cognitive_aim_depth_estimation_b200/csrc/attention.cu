@@ -1,19 +1,26 @@
 // Flash-style multi-head self-attention forward for the DINOv2 backbone on sm_100a (head_dim 64, no mask).
 // Replaces `F.scaled_dot_product_attention` at HF modeling_dinov2.py:215-229 (scale 64^-0.5, softmax over keys).
 //
-// One CTA = one (image, head) x one tile of 128 queries; two CTAs co-reside per SM (112 KB smem, 256 TMEM
-// columns each) so that one CTA's softmax (MUFU-bound) overlaps the other's tensor-core work.
+// The kernel is MUFU-bound (one exp2 per score: 16 /clk/SM against 8192 tensor flops/clk/SM), so the design goal
+// is to keep FOUR softmax warps resident per SM sub-partition, each running a short serial chain, instead of
+// making one warp fast.  One CTA = one (image, head) x one tile of 128 queries; two CTAs co-reside per SM
+// (112 KB smem, 256 TMEM columns each).  Inside a CTA the key axis is cut into 64-key steps which are dealt
+// alternately to two independent STREAMS (even steps / odd steps).  A stream owns an S buffer and an O accumulator
+// in TMEM, a P buffer in smem, its own softmax reference (m, l), its own MMA-issuing warp and softmax warpgroup;
+// the two partial results are merged in the epilogue (flash-decoding style split over keys, inside the CTA).
 //
-//   warp 0     : TMA producer — Q once, then K/V tiles of 128 keys into a 2-stage ring (128B swizzle)
-//   warp 1     : MMA issuer   — S = Q K^T   (tcgen05.mma 128x128x16 x4, both operands K-major)
-//                               O += P V    (tcgen05.mma 128x64x16  x8, P K-major from smem, V MN-major as loaded)
-//                               owns the TMEM allocation (S: 128 fp32 columns, O: 64 fp32 columns)
-//   warps 2..5 : softmax      — one query row per thread: tcgen05.ld S, online max / sum in fp32 (base-2 domain),
-//                               P -> bf16 -> swizzled smem, rescale O in TMEM when the running max moved,
-//                               final O / l -> bf16 -> global (token-major, head h at columns [64h, 64h+64))
+//   warp 0      : TMA producer — Q once; K and V steps (64 keys = 8 KB each) into two 4-slot rings
+//                 (K runs two steps ahead of V, the order the tensor core consumes them in)
+//   warp 1+s    : MMA issuer of stream s — S_i = Q K_i^T (tcgen05.mma 128x64x16 x4) as soon as the softmax warps have
+//                 pulled S_{i-2} out of TMEM; O_s += P_i V_i (128x64x16 x4, P K-major from smem, V MN-major as loaded)
+//   warp 3      : idle (keeps the control warps one aligned warpgroup for setmaxnreg)
+//   warps 4+4s..: softmax of stream s — one query row per thread: the 64-wide S_i row is pulled into registers and
+//                 the TMEM buffer handed back at once; exact row max in registers; the accumulator reference moves
+//                 only when a row grew by more than 2^8 (lazy rescale); P = exp2(s*scale - ref) -> bf16 -> swizzled
+//                 smem.  Registers are re-budgeted with setmaxnreg (control warps 32, softmax warps 104).
 //
 // Input is the fused QKV activation [B*T, 3*H*64] written by the QKV GEMM (Q | K | V column blocks), read in place
-// through one 3-D tensor map (col, token, image): no head-major reshuffle pass exists.
+// through 3-D tensor maps (col, token, image): no head-major reshuffle pass exists.
 #include "attention.cuh"
 #include "common.cuh"
 #include "host.h"
@@ -25,190 +32,70 @@ namespace {
 
 constexpr int kHeadDim = 64;
 constexpr int kTileQ = 128;
-constexpr int kTileK = 128;
-constexpr int kKVStages = 2;
-constexpr int kAttnThreads = 6 * 32;
-constexpr int kTileBytes = 128 * kHeadDim * 2;                 // 16 KB: 128 rows x 128 B
+constexpr int kSubK = 64;                          // keys per pipeline step
+constexpr int kRing = 4;                           // K ring slots == V ring slots
+constexpr int kAttnThreads = 12 * 32;
+constexpr int kQBytes = kTileQ * kHeadDim * 2;     // 16 KB: 128 rows x 128 B
+constexpr int kSubBytes = kSubK * kHeadDim * 2;    // 8 KB: 64 rows x 128 B
+constexpr int kPBytes = kTileQ * kSubK * 2;        // 16 KB: 128 rows x 128 B (64 keys)
 constexpr int kSmemQ = 0;
-constexpr int kSmemK = kSmemQ + kTileBytes;
-constexpr int kSmemV = kSmemK + kKVStages * kTileBytes;
-constexpr int kSmemP = kSmemV + kKVStages * kTileBytes;          // 2 chunks of 64 keys
-constexpr int kSmemBar = kSmemP + 2 * kTileBytes;
-constexpr int kAttnSmemBytes = kSmemBar + 128;
+constexpr int kSmemK = kSmemQ + kQBytes;
+constexpr int kSmemV = kSmemK + kRing * kSubBytes;
+constexpr int kSmemP = kSmemV + kRing * kSubBytes;   // one P buffer per stream
+constexpr int kSmemStats = kSmemQ;                   // epilogue only (Q is dead by then): float2 (m, l) [2][128]
+constexpr int kSmemBar = kSmemP + 2 * kPBytes;
+constexpr int kAttnSmemBytes = kSmemBar + 256;
 constexpr uint32_t kTmemCols = 256;
-constexpr uint32_t kTmemS = 0;
-constexpr uint32_t kTmemO = 128;
+constexpr uint32_t kTmemS = 0;      // S buffer of stream s: 64 fp32 columns at 64 s
+constexpr uint32_t kTmemO = 128;    // O accumulator of stream s: 64 fp32 columns at 128 + 64 s
+constexpr float kLazyLimit = 8.0f;  // the accumulator reference moves only when a row max grew by > 2^8
+static_assert(2 * (kAttnSmemBytes + 1024) <= 227 * 1024, "two CTAs must fit one SM");
+constexpr int kCtrlRegs = 32;
+constexpr int kSoftmaxRegs = 104;
 
 struct AttnArgs {
   int T;          // tokens per image
   int H;          // heads
-  int n_kv;       // key tiles
+  int n_sub;      // 64-key steps
   float scale_log2;
   __nv_bfloat16* out;  // [B*T, H*64]
   int ldo;
-  int dbg;  // CA_ATTN_DEBUG timing experiments (results are garbage when non-zero)
-  long long* trace;  // CA_ATTN_TRACE=1: per-tile clock64 stamps of CTA (5, 40) [n_kv][10]
 };
-#define CA_TRACE(slot)                                                                                  \
-  if (p.trace && blockIdx.x == 5 && blockIdx.y == 40) p.trace[j * 10 + (slot)] = clock64();
 
-
-// One softmax step for one query row (thread) over a 128-key S tile held in TMEM:
-//   pass 1: row max of the raw accumulators (4 independent chains, no per-element scaling)
-//   pass 2: P = exp2(s*scale - max) -> bf16 -> 128B-swizzled smem (A operand of the PV MMA), fp32 row sum
-// TMEM loads are software-pipelined (chunk c+1 is in flight while chunk c is processed).  kMasked is only
-// instantiated for the ragged last tile, so the steady-state path carries no predicates.
-template <bool kMasked>
-__device__ __forceinline__ float softmax_tile(uint32_t t_s, uint8_t* p_row, int r, int valid, float scale_log2,
-                                              float m_run, float& sum_out, int dbg, uint64_t* s_free,
-                                              uint64_t* pv_done, int j) {
-  uint32_t v[2][32];
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-  tmem_ld32(t_s, v[0]);
-  if (dbg & 1) { m0 = 0.f; }
-  else
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    tmem_ld_wait();
-    if (c < 3) tmem_ld32(t_s + (c + 1) * 32, v[(c + 1) & 1]);
-    else tmem_ld32(t_s, v[0]);  // chunk 0 again for pass 2
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float x0 = __uint_as_float(v[c & 1][i + 0]), x1 = __uint_as_float(v[c & 1][i + 1]);
-      float x2 = __uint_as_float(v[c & 1][i + 2]), x3 = __uint_as_float(v[c & 1][i + 3]);
-      if (kMasked) {
-        x0 = (c * 32 + i + 0 < valid) ? x0 : -INFINITY;
-        x1 = (c * 32 + i + 1 < valid) ? x1 : -INFINITY;
-        x2 = (c * 32 + i + 2 < valid) ? x2 : -INFINITY;
-        x3 = (c * 32 + i + 3 < valid) ? x3 : -INFINITY;
-      }
-      m0 = fmaxf(m0, x0);
-      m1 = fmaxf(m1, x1);
-      m2 = fmaxf(m2, x2);
-      m3 = fmaxf(m3, x3);
-    }
-  }
-  if (dbg & 1) { tmem_ld_wait(); tmem_ld32(t_s, v[0]); }
-  const float mx = fmaxf(m_run, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale_log2);  // scale_log2 > 0
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    tmem_ld_wait();
-    if (c < 3) {
-      tmem_ld32(t_s + (c + 1) * 32, v[(c + 1) & 1]);
-    } else {  // S_j is now entirely in registers: let the MMA warp overwrite it with S_{j+1}
-      tc_fence_before();
-      __syncwarp();
-      if (lane_id() == 0) mbar_arrive(s_free);
-    }
-    if (c == 0 && j > 0) mbar_wait(pv_done, (j - 1) & 1);  // P_{j-1} V_{j-1} finished: P buffer and O are ours again
-    uint8_t* chunk_base = p_row + (c >> 1) * kTileBytes;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float e[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        e[i] = (dbg & 2) ? fmaf(__uint_as_float(v[c & 1][8 * t + i]), scale_log2, -mx)
-                         : fast_exp2(fmaf(__uint_as_float(v[c & 1][8 * t + i]), scale_log2, -mx));
-        if (kMasked) e[i] = (c * 32 + 8 * t + i < valid) ? e[i] : 0.f;
-      }
-      s0 += e[0] + e[4];
-      s1 += e[1] + e[5];
-      s2 += e[2] + e[6];
-      s3 += e[3] + e[7];
-      uint4 w;
-      w.x = pack_bf16x2(e[0], e[1]);
-      w.y = pack_bf16x2(e[2], e[3]);
-      w.z = pack_bf16x2(e[4], e[5]);
-      w.w = pack_bf16x2(e[6], e[7]);
-      if (!(dbg & 4)) *reinterpret_cast<uint4*>(chunk_base + sw128_offset(r, (c & 1) * 4 + t)) = w;
-    }
-  }
-  sum_out = (s0 + s1) + (s2 + s3);
-  return mx;
+// d = a * s + c on two packed fp32 lanes (FFMA2)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float s, float c) {
+  asm("{\n\t.reg .b64 ra, rs, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rs, {%4, %4};\n\tmov.b64 rc, {%5, %5};\n\t"
+      "fma.rn.f32x2 rd, ra, rs, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(s), "f"(c));
 }
-
-// Steady-state softmax step: ONE pass over the S tile (TMEM read bandwidth, 64 B/clk/SM, is as scarce here as the
-// MUFU).  The exponent reference `m_use` is the running max of the PREVIOUS tiles, so exp2 needs no max pass; the
-// max of this tile is gathered on the side for the next tile.  Returns false — without having signalled s_free —
-// when some row of the warp exceeds the reference by more than 2^kLagLimit; the caller then redoes the tile with
-// the exact two-pass path (always the case for the first tile, whose reference is -inf).
-constexpr float kLagLimit = 16.0f;
-template <bool kMasked>
-__device__ __forceinline__ bool softmax_tile_fast(uint32_t t_s, uint8_t* p_row, int r, int valid, float scale_log2,
-                                                  float m_use, float& sum_out, float& tile_max, uint64_t* s_free,
-                                                  uint64_t* pv_done, int j) {
-  uint32_t v[2][32];
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  bool ok = true;
-  tmem_ld32(t_s, v[0]);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    tmem_ld_wait();
-    if (c < 3) tmem_ld32(t_s + (c + 1) * 32, v[(c + 1) & 1]);
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float x0 = __uint_as_float(v[c & 1][i + 0]), x1 = __uint_as_float(v[c & 1][i + 1]);
-      float x2 = __uint_as_float(v[c & 1][i + 2]), x3 = __uint_as_float(v[c & 1][i + 3]);
-      if (kMasked) {
-        x0 = (c * 32 + i + 0 < valid) ? x0 : -INFINITY;
-        x1 = (c * 32 + i + 1 < valid) ? x1 : -INFINITY;
-        x2 = (c * 32 + i + 2 < valid) ? x2 : -INFINITY;
-        x3 = (c * 32 + i + 3 < valid) ? x3 : -INFINITY;
-      }
-      m0 = fmaxf(m0, x0);
-      m1 = fmaxf(m1, x1);
-      m2 = fmaxf(m2, x2);
-      m3 = fmaxf(m3, x3);
-    }
-    if (c == 3) {  // whole tile seen: decide, and hand S back to the tensor core as early as possible
-      tile_max = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale_log2;
-      ok = !__any_sync(0xffffffffu, tile_max > m_use + kLagLimit);
-      if (!ok) return false;
-      tc_fence_before();
-      __syncwarp();
-      if (lane_id() == 0) mbar_arrive(s_free);
-    }
-    if (c == 0) mbar_wait(pv_done, (j - 1) & 1);  // P_{j-1} V_{j-1} finished: the P buffer is ours again (j > 0 here)
-    uint8_t* chunk_base = p_row + (c >> 1) * kTileBytes;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float e[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        e[i] = fast_exp2(fmaf(__uint_as_float(v[c & 1][8 * t + i]), scale_log2, -m_use));
-        if (kMasked) e[i] = (c * 32 + 8 * t + i < valid) ? e[i] : 0.f;
-      }
-      s0 += e[0] + e[4];
-      s1 += e[1] + e[5];
-      s2 += e[2] + e[6];
-      s3 += e[3] + e[7];
-      uint4 w;
-      w.x = pack_bf16x2(e[0], e[1]);
-      w.y = pack_bf16x2(e[2], e[3]);
-      w.z = pack_bf16x2(e[4], e[5]);
-      w.w = pack_bf16x2(e[6], e[7]);
-      *reinterpret_cast<uint4*>(chunk_base + sw128_offset(r, (c & 1) * 4 + t)) = w;
-    }
-  }
-  sum_out = (s0 + s1) + (s2 + s3);
-  return true;
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {
+  asm("{\n\t.reg .b64 ra, rd;\n\t"
+      "mov.b64 rd, {%0, %1};\n\tmov.b64 ra, {%2, %3};\n\t"
+      "add.rn.f32x2 rd, rd, ra;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1));
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
-attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) {
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                     const AttnArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;   // MMA -> softmax : S_j is in TMEM
-  uint64_t* p_full = bars + 6;   // softmax -> MMA : P_j is in smem and O is rescaled
-  uint64_t* o_full = bars + 7;   // MMA -> softmax : last P V finished
-  uint64_t* s_free = bars + 8;   // softmax -> MMA : S_j has been read out of TMEM (S_{j+1} may overwrite it)
-  uint64_t* pv_done = bars + 9;  // MMA -> softmax : P_j V_j finished (P buffer and O may be touched again)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* k_full = bars + 1;     // [4] TMA -> MMA
+  uint64_t* k_empty = bars + 5;    // [4] MMA (commit) -> TMA
+  uint64_t* v_full = bars + 9;     // [4]
+  uint64_t* v_empty = bars + 13;   // [4]
+  uint64_t* s_full = bars + 17;    // [stream] MMA -> softmax : S of the stream's current step is in TMEM
+  uint64_t* s_free = bars + 19;    // [stream] softmax -> MMA : that S is in registers, the buffer may be overwritten
+  uint64_t* p_full = bars + 21;    // [stream] softmax -> MMA : P is in smem (and O_s is rescaled)
+  uint64_t* p_free = bars + 23;    // [stream] MMA -> softmax : P V finished (P buffer reusable, O_s quiescent)
+  uint64_t* o_full = bars + 25;    // [stream] MMA -> softmax : the stream's last P V finished
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
 
   const int warp = warp_id();
   const int lane = lane_id();
@@ -220,23 +107,29 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArg
   const int col_q = h * kHeadDim;
   const int col_k = (p.H + h) * kHeadDim;
   const int col_v = (2 * p.H + h) * kHeadDim;
+  const int n_sub = p.n_sub;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
       printf("[cogaim] attention: dynamic smem base not 1024-byte aligned\n");
       __trap();
     }
-    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
     mbar_init(q_full, 1);
-    for (int s = 0; s < kKVStages; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+    for (int s = 0; s < kRing; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
-    mbar_init(s_free, 4);
-    mbar_init(pv_done, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_free[s], 4);
+      mbar_init(&p_full[s], 4);
+      mbar_init(&p_free[s], 1);
+      mbar_init(&o_full[s], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -245,151 +138,220 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArg
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kTileBytes);
-      tma_load_3d(smem + kSmemQ, &tmap_qkv, q_full, col_q, q0, b);
-      for (int j = 0; j < p.n_kv; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1u);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * kTileBytes);
-        tma_load_3d(smem + kSmemK + s * kTileBytes, &tmap_qkv, &kv_full[s], col_k, j * kTileK, b);
-        tma_load_3d(smem + kSmemV + s * kTileBytes, &tmap_qkv, &kv_full[s], col_v, j * kTileK, b);
+  if (warp < 4) {
+    setmaxnreg_dec<kCtrlRegs>();
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, kQBytes);
+        tma_load_3d(smem + kSmemQ, &tmap_q, q_full, col_q, q0, b);
+        auto load_k = [&](int i) {
+          const int s = i & (kRing - 1);
+          mbar_wait(&k_empty[s], ((i / kRing) & 1) ^ 1u);
+          mbar_arrive_expect_tx(&k_full[s], kSubBytes);
+          tma_load_3d(smem + kSmemK + s * kSubBytes, &tmap_kv, &k_full[s], col_k, i * kSubK, b);
+        };
+        load_k(0);
+        if (n_sub > 1) load_k(1);
+        for (int i = 0; i < n_sub; ++i) {
+          const int s = i & (kRing - 1);
+          mbar_wait(&v_empty[s], ((i / kRing) & 1) ^ 1u);
+          mbar_arrive_expect_tx(&v_full[s], kSubBytes);
+          tma_load_3d(smem + kSmemV + s * kSubBytes, &tmap_kv, &v_full[s], col_v, i * kSubK, b);
+          if (i + 2 < n_sub) load_k(i + 2);
+        }
       }
-    }
-  } else if (warp == 1) {
-    // All 32 lanes walk the protocol (waits are cheap); the tensor-core instructions are issued by one elected lane.
-    // Order on the (in-order) tensor pipe:  S_0 | S_1 PV_0 | S_2 PV_1 | ...   S_{j+1} is issued as soon as the softmax
-    // warps have pulled S_j out of TMEM, so it runs under their exp / store phase and is off the critical path.
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);  // B (=V) is MN-major
-    const uint64_t qd = umma_smem_desc_sw128(smem_u32(smem + kSmemQ));
-    const uint64_t kd0 = umma_smem_desc_sw128(smem_u32(smem + kSmemK));
-    const uint64_t pd0 = umma_smem_desc_sw128(smem_u32(smem + kSmemP));
-    const uint64_t vd0 = umma_smem_desc_sw128(smem_u32(smem + kSmemV), 1024, 1024);
-    constexpr uint64_t kStageStep = kTileBytes >> 4;  // descriptor address units are 16 bytes
-    mbar_wait(q_full, 0);
-    mbar_wait(&kv_full[0], 0);
-    tc_fence_after();
-    if (elect_one_sync()) {
-#pragma unroll
-      for (int k = 0; k < kHeadDim / 16; ++k) umma_bf16(tmem_base + kTmemS, qd + 2 * k, kd0 + 2 * k, idesc_s, k != 0);
-      umma_commit(s_full);
-    }
-    __syncwarp();
-    for (int j = 0; j < p.n_kv; ++j) {
-      const int s = j & 1;
-      if (j + 1 < p.n_kv) {
-        mbar_wait(&kv_full[s ^ 1], ((j + 1) >> 1) & 1);
-        mbar_wait(s_free, j & 1);
+    } else if (warp <= 2) {
+      // MMA issuer of stream st.  All 32 lanes walk the protocol; the tensor-core instructions are issued by one
+      // elected lane.  Issue order per stream:  S_0 | S_1 PV_0 | S_2 PV_1 | ...  (steps counted inside the stream).
+      const int st = warp - 1;
+      const int n_st = (n_sub - st + 1) >> 1;  // steps of this stream
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kSubK, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);  // B (=V) is MN-major
+      const uint64_t qd = umma_smem_desc_sw128(smem_u32(smem + kSmemQ));
+      const uint64_t kd0 = umma_smem_desc_sw128(smem_u32(smem + kSmemK));
+      const uint64_t pd = umma_smem_desc_sw128(smem_u32(smem + kSmemP + st * kPBytes));
+      const uint64_t vd0 = umma_smem_desc_sw128(smem_u32(smem + kSmemV), 1024, 1024);
+      constexpr uint64_t kSubStep = kSubBytes >> 4;  // descriptor address units are 16 bytes
+      const uint32_t d_s = tmem_base + kTmemS + st * kSubK;
+      const uint32_t d_o = tmem_base + kTmemO + st * kHeadDim;
+      auto issue_s = [&](int i) {
+        const int s = i & (kRing - 1);
+        mbar_wait(&k_full[s], (i / kRing) & 1);
         tc_fence_after();
-        CA_TRACE(0)
         if (elect_one_sync()) {
-          const uint64_t kd = kd0 + (s ^ 1) * kStageStep;
+          const uint64_t kd = kd0 + s * kSubStep;
 #pragma unroll
-          for (int k = 0; k < kHeadDim / 16; ++k) umma_bf16(tmem_base + kTmemS, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
-          umma_commit(s_full);
+          for (int k = 0; k < kHeadDim / 16; ++k) umma_bf16(d_s, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[st]);
+          umma_commit(&k_empty[s]);
         }
         __syncwarp();
-        CA_TRACE(1)
+      };
+      if (n_st > 0) {
+        mbar_wait(q_full, 0);
+        issue_s(st);
       }
-      mbar_wait(p_full, j & 1);
-      tc_fence_after();
-      CA_TRACE(2)
-      if (elect_one_sync()) {
-        const uint64_t vd = vd0 + s * kStageStep;
-#pragma unroll
-        for (int k = 0; k < kTileK / 16; ++k) {
-          // P: 64-key chunk (k >> 2), +32 B per 16 keys inside the swizzle atom; V: 16 keys = 2048 B further down
-          umma_bf16(tmem_base + kTmemO, pd0 + (k >> 2) * kStageStep + 2 * (k & 3), vd + k * (2048 >> 4), idesc_o,
-                    (j | k) != 0);
+      for (int n = 0; n < n_st; ++n) {
+        const int i = 2 * n + st;
+        const int s = i & (kRing - 1);
+        if (n + 1 < n_st) {
+          mbar_wait(&s_free[st], n & 1);  // S_i has been read out of TMEM
+          issue_s(i + 2);
         }
-        umma_commit(&kv_empty[s]);
-        umma_commit(pv_done);
-        if (j == p.n_kv - 1) umma_commit(o_full);
+        mbar_wait(&v_full[s], (i / kRing) & 1);
+        mbar_wait(&p_full[st], n & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t vd = vd0 + s * kSubStep;
+#pragma unroll
+          for (int k = 0; k < kSubK / 16; ++k) {
+            // P: +32 B per 16 keys inside the swizzle atom; V: 16 keys = 16 rows of 128 B = 2048 B further down
+            umma_bf16(d_o, pd + 2 * k, vd + k * (2048 >> 4), idesc_o, (n | k) != 0);
+          }
+          umma_commit(&p_free[st]);
+          umma_commit(&v_empty[s]);
+          if (n == n_st - 1) umma_commit(&o_full[st]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      CA_TRACE(3)
     }
   } else {
+    setmaxnreg_inc<kSoftmaxRegs>();
+    const int st = (warp - 4) >> 2;
+    const int n_st = (n_sub - st + 1) >> 1;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;  // query row inside the tile == TMEM lane
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + kTmemS;
-    const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + kTmemO;
-    uint8_t* p_row = smem + kSmemP;
-    float m_hint = -INFINITY;  // running row max over the tiles seen so far
-    float m_acc = -INFINITY;   // reference the O accumulator and l_run are currently expressed in
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t t_s = t_lane + kTmemS + st * kSubK;
+    const uint32_t t_o = t_lane + kTmemO + st * kHeadDim;
+    uint8_t* p_buf = smem + kSmemP + st * kPBytes;
+    const float scale = p.scale_log2;
+    float m_acc = -INFINITY;  // reference (log2 domain) O_s and l_run are expressed in
     float l_run = 0.f;
-    for (int j = 0; j < p.n_kv; ++j) {
-      const int valid = p.T - j * kTileK;  // >= 128 on every tile but the last
-      mbar_wait(s_full, j & 1);
+    for (int n = 0; n < n_st; ++n) {
+      const int valid = p.T - (2 * n + st) * kSubK;  // >= 64 on every step but the last
+      uint32_t v[64];
+      mbar_wait(&s_full[st], n & 1);
       tc_fence_after();
-      if (threadIdx.x == 64) { CA_TRACE(4) }
-      // Exponent reference of this tile: the running max of the previous tiles (single-pass fast path), or the exact
-      // max including this tile (two-pass path: first tile, or a row jumped by more than 2^kLagLimit).
-      float m_use = m_hint, sum, tile_max = -INFINITY;
-      bool done = false;
-      if (j > 0 && !(p.dbg & 16)) {
-        done = (valid >= kTileK)
-                   ? softmax_tile_fast<false>(t_s, p_row, r, kTileK, p.scale_log2, m_use, sum, tile_max, s_free, pv_done, j)
-                   : softmax_tile_fast<true>(t_s, p_row, r, valid, p.scale_log2, m_use, sum, tile_max, s_free, pv_done, j);
+      {
+        uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+        uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+        tmem_ld32(t_s, v0);
+        tmem_ld32(t_s + 32, v1);
+        tmem_ld_wait();
       }
-      if (!done) {
-        m_use = (valid >= kTileK)
-                    ? softmax_tile<false>(t_s, p_row, r, kTileK, p.scale_log2, m_hint, sum, p.dbg, s_free, pv_done, j)
-                    : softmax_tile<true>(t_s, p_row, r, valid, p.scale_log2, m_hint, sum, p.dbg, s_free, pv_done, j);
-        tile_max = m_use;
-      }
-      const float alpha = fast_exp2(m_acc - m_use);  // O and l are expressed relative to m_acc; 0 on the first tile
-      if (threadIdx.x == 64) { CA_TRACE(5) }
-      l_run = l_run * alpha + sum;
-      m_acc = m_use;
-      m_hint = fmaxf(m_hint, tile_max);
-      // ---- rescale the O accumulator when any row of this warp moved its max (warp-uniform branch) ----
-      if (j > 0 && !(p.dbg & 8) && __any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_o + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st32(t_o + c * 32, v);
-        }
-        tmem_st_wait();
-      }
-      if (threadIdx.x == 64) { CA_TRACE(6) }
-      fence_proxy_async_smem();  // P visible to the tensor-core (async) proxy
-      if (threadIdx.x == 64) { CA_TRACE(7) }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      if (threadIdx.x == 64) { CA_TRACE(8) }
-    }
-    // ---- epilogue: O / l -> bf16 -> global ----
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const float inv = 1.0f / l_run;
-    const int q = q0 + r;
-    __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * p.T + q) * p.ldo + h * kHeadDim;
+      if (lane == 0) mbar_arrive(&s_free[st]);  // S lives in registers now: the stream's next S may overwrite it
+      if (valid < kSubK) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld32(t_o + c * 32, v);
-      tmem_ld_wait();
-      if (q < p.T) {
-        uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
+        for (int c = 0; c < kSubK; ++c)
+          if (c >= valid) v[c] = 0xff800000u;  // -inf: exp2 -> 0, ignored by the max
+      }
+      // ---- exact row max, four independent chains ----
+      float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]),
+            m3 = __uint_as_float(v[3]);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(v[8 * t + 0]) * inv, __uint_as_float(v[8 * t + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(v[8 * t + 2]) * inv, __uint_as_float(v[8 * t + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(v[8 * t + 4]) * inv, __uint_as_float(v[8 * t + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(v[8 * t + 6]) * inv, __uint_as_float(v[8 * t + 7]) * inv);
-          o4[t] = w;
+      for (int c = 4; c < kSubK; c += 8) {
+        m0 = fmaxf(m0, fmaxf(__uint_as_float(v[c + 0]), __uint_as_float(v[c + 1])));
+        m1 = fmaxf(m1, fmaxf(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])));
+        if (c + 4 < kSubK) {
+          m2 = fmaxf(m2, fmaxf(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5])));
+          m3 = fmaxf(m3, fmaxf(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7])));
         }
       }
+      const float tile_max = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale;  // scale > 0
+      if (n > 0) mbar_wait(&p_free[st], (n - 1) & 1);  // previous P V of the stream finished: P buffer ours, O_s quiet
+      // ---- lazy reference update (warp-uniform decision; always taken on the first step) ----
+      if (__any_sync(0xffffffffu, tile_max > m_acc + kLazyLimit)) {
+        const float m_new = fmaxf(m_acc, tile_max);
+        const float alpha = fast_exp2(m_acc - m_new);  // 0 on the first step (m_acc = -inf)
+        l_run *= alpha;
+        m_acc = m_new;
+        if (n > 0) {
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[16];
+            tmem_ld16(t_o + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+            tmem_st16(t_o + c * 16, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // ---- P = exp2(s * scale - m_acc) -> bf16 -> swizzled smem ; fp32 row sum ----
+      const float neg_m = -m_acc;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int t = 0; t < kSubK / 8; ++t) {
+        float e[8];
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+          ffma2(e[k], e[k + 1], __uint_as_float(v[8 * t + k]), __uint_as_float(v[8 * t + k + 1]), scale, neg_m);
+          e[k] = fast_exp2(e[k]);
+          e[k + 1] = fast_exp2(e[k + 1]);
+        }
+        fadd2(s0, s1, e[0], e[1]);
+        fadd2(s2, s3, e[2], e[3]);
+        fadd2(s0, s1, e[4], e[5]);
+        fadd2(s2, s3, e[6], e[7]);
+        uint4 w;
+        w.x = pack_bf16x2(e[0], e[1]);
+        w.y = pack_bf16x2(e[2], e[3]);
+        w.z = pack_bf16x2(e[4], e[5]);
+        w.w = pack_bf16x2(e[6], e[7]);
+        *reinterpret_cast<uint4*>(p_buf + sw128_offset(r, t)) = w;
+      }
+      l_run += (s0 + s1) + (s2 + s3);
+      fence_proxy_async_smem();  // P visible to the tensor-core (async) proxy
+      tc_fence_before();         // orders the O rescale (tcgen05.st) before the PV issue
       __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[st]);
+    }
+    // ---- epilogue: merge the two streams, O / l -> bf16 -> global.  Stream st writes head dims [32 st, 32 st + 32). ----
+    float2* stats = reinterpret_cast<float2*>(smem + kSmemStats);
+    const int n_other = (n_sub - (st ^ 1) + 1) >> 1;
+    if (n_st > 0) mbar_wait(&o_full[st], 0);  // every tensor-core op of the stream has finished (Q is dead, O_s final)
+    if (n_other > 0) mbar_wait(&o_full[st ^ 1], 0);
+    tc_fence_after();
+    stats[st * kTileQ + r] = make_float2(m_acc, l_run);
+    named_bar_sync(1, 8 * 32);
+    const float2 other = stats[(st ^ 1) * kTileQ + r];
+    const float m_all = fmaxf(m_acc, other.x);
+    const float a_self = fast_exp2(m_acc - m_all), a_other = fast_exp2(other.x - m_all);
+    const float inv = 1.0f / (l_run * a_self + other.y * a_other);
+    const float w_self = a_self * inv, w_other = a_other * inv;
+    const int q = q0 + r;
+    uint32_t os[32], oo[32];
+    tmem_ld32(t_lane + kTmemO + st * kHeadDim + st * 32, os);
+    if (n_other > 0) tmem_ld32(t_lane + kTmemO + (st ^ 1) * kHeadDim + st * 32, oo);
+    tmem_ld_wait();
+    if (n_other == 0 || n_st == 0) {  // an empty stream's accumulator was never written
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        if (n_other == 0) oo[k] = 0u;
+        if (n_st == 0) os[k] = 0u;
+      }
+    }
+    if (q < p.T) {
+      __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * p.T + q) * p.ldo + h * kHeadDim + st * 32;
+      uint4* o4 = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          f[k] = __uint_as_float(os[8 * t + k]) * w_self + __uint_as_float(oo[8 * t + k]) * w_other;
+        uint4 w;
+        w.x = pack_bf16x2(f[0], f[1]);
+        w.y = pack_bf16x2(f[2], f[3]);
+        w.z = pack_bf16x2(f[4], f[5]);
+        w.w = pack_bf16x2(f[6], f[7]);
+        o4[t] = w;
+      }
     }
   }
 
@@ -407,8 +369,9 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
   CA_REQUIRE(qkv && out, "attention: null pointer");
   CA_REQUIRE(B > 0 && T > 0 && H > 0, "attention: non-positive dimension");
   const int ld = 3 * H * kHeadDim;
-  CUtensorMap tm;
-  CA_TRY(make_tmap_3d(&tm, qkv, B, T, ld, ld, static_cast<uint64_t>(T) * ld, 128));
+  CUtensorMap tm_q, tm_kv;
+  CA_TRY(make_tmap_3d(&tm_q, qkv, B, T, ld, ld, static_cast<uint64_t>(T) * ld, kTileQ));
+  CA_TRY(make_tmap_3d(&tm_kv, qkv, B, T, ld, ld, static_cast<uint64_t>(T) * ld, kSubK));
   static bool configured = false;
   if (!configured) {
     CA_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
@@ -417,37 +380,13 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
   AttnArgs a;
   a.T = T;
   a.H = H;
-  a.n_kv = (T + kTileK - 1) / kTileK;
+  a.n_sub = (T + kSubK - 1) / kSubK;
   a.scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
   a.out = out;
   a.ldo = H * kHeadDim;
-  static const int dbg = getenv("CA_ATTN_DEBUG") ? atoi(getenv("CA_ATTN_DEBUG")) : 0;
-  a.dbg = dbg;
-  a.trace = nullptr;
-  static const bool want_trace = getenv("CA_ATTN_TRACE") != nullptr;
-  static long long* d_trace = nullptr;
-  if (want_trace) {
-    if (!d_trace) CA_CUDA(cudaMalloc(&d_trace, 64 * 10 * sizeof(long long)));
-    CA_CUDA(cudaMemsetAsync(d_trace, 0, 64 * 10 * sizeof(long long), stream));
-    a.trace = d_trace;
-  }
   dim3 grid((T + kTileQ - 1) / kTileQ, B * H);
-  attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tm, a);
+  attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tm_q, tm_kv, a);
   CA_CUDA(cudaGetLastError());
-  if (want_trace) {
-    static int dumps = 0;
-    long long h[64 * 10];
-    CA_CUDA(cudaStreamSynchronize(stream));
-    CA_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
-    if (dumps++ == 4) {
-      const long long t0 = h[0];
-      for (int j = 0; j < a.n_kv && j < 64; ++j) {
-        fprintf(stderr, "tile %2d:", j);
-        for (int k = 0; k < 9; ++k) fprintf(stderr, " %7lld", h[j * 10 + k] - t0);
-        fprintf(stderr, "\n");
-      }
-    }
-  }
   return 0;
 }
 
