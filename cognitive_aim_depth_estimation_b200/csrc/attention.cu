@@ -7,8 +7,11 @@
 // live in TMEM: Q (stored once per CTA) and P (written by the softmax warps over the S columns they just read);
 // shared memory only carries the K / V stream (TMA in, one tensor-core read each).
 //
-// One CTA = one (image, head) x one tile of 128 queries; two CTAs co-reside per SM (64 KB smem, 256 TMEM columns
-// each).  The key axis is walked in steps of 64 keys, S double-buffered in TMEM:
+// Work item = one (image, head) x one tile of 128 queries.  The kernel is PERSISTENT: two CTAs co-reside per SM
+// (64 KB smem, 256 TMEM columns each) and each walks items blockIdx.x, blockIdx.x + gridDim.x, ... as ONE flattened
+// sequence of 64-key steps, so the K/V stream, the S MMAs and the Q tile of the next item are already in flight
+// while the current item finishes (a per-item launch loses ~20 % to TMEM allocation, first-load latency and the
+// drain of the last P V at T = 1370).  S is double-buffered in TMEM, Q double-buffered per item:
 //
 //   warp 0     : TMA producer — K and V steps (64 keys = 8 KB each) into two independent 4-slot rings
 //                (K runs two steps ahead of V, the order the tensor core consumes them in)
@@ -16,7 +19,9 @@
 //                               O += P_i V_i   (tcgen05.mma 128x64x16 x4, A = P_i in TMEM, V MN-major as loaded)
 //                               issue order S_0 S_1 | PV_0 S_2 | PV_1 S_3 | ...  (S_{i+2} overwrites the buffer that held
 //                               S_i / P_i; the tensor pipe executes in issue order, so it follows PV_i's operand reads)
-//   warps 2..5 : softmax      — one query row per thread: Q row global -> TMEM once; per step the 64-wide S_i row is
+//   warps 2..5 : softmax      — one query row per thread: Q row global -> TMEM (for the NEXT item, one item ahead); the
+//                               epilogue of item k (O / l -> global) runs inside step 0 of item k+1, after that step's
+//                               exponentials, so the drain of the last P V is hidden; per step the 64-wide S_i row is
 //                               pulled into registers (two tcgen05.ld), exact row max in registers, the accumulator
 //                               reference only moves when a row grew by more than 2^8 (lazy rescale),
 //                               P = exp2(s*scale - ref) -> bf16x2 -> tcgen05.st over the first 32 columns of the buffer.
@@ -29,35 +34,48 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace ca {
 namespace {
 
 constexpr int kHeadDim = 64;
 constexpr int kTileQ = 128;
 constexpr int kSubK = 64;                          // keys per pipeline step
-constexpr int kRing = 4;                           // K ring slots == V ring slots
+constexpr int kRing = 6;                           // K ring slots == V ring slots
 constexpr int kAttnThreads = 6 * 32;
 constexpr int kSubBytes = kSubK * kHeadDim * 2;    // 8 KB: 64 rows x 128 B
 constexpr int kSmemK = 0;
 constexpr int kSmemV = kSmemK + kRing * kSubBytes;
 constexpr int kSmemBar = kSmemV + kRing * kSubBytes;
-constexpr int kAttnSmemBytes = kSmemBar + 256;
+constexpr int kAttnSmemBytes = kSmemBar + 512;
 static_assert(2 * (kAttnSmemBytes + 1024) <= 227 * 1024, "two CTAs must fit one SM");
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kTmemS = 0;      // two S buffers of 64 fp32 columns; P_i (bf16x2) overwrites the first 32 of buffer i&1
 constexpr uint32_t kTmemO = 128;    // 64 fp32 columns
-constexpr uint32_t kTmemQ = 192;    // 32 columns: Q tile as bf16x2 (A operand of every S MMA)
+constexpr uint32_t kTmemQ = 192;    // 2 x 32 columns: Q tile of item k&1 as bf16x2 (A operand of every S MMA)
+constexpr int kItemQ = 8;            // depth of the per-CTA item queue (power of two)
+#ifndef CA_ATTN_POLY_PAIRS
+#define CA_ATTN_POLY_PAIRS 1
+#endif
+constexpr int kPolyPairs = CA_ATTN_POLY_PAIRS;  // of every 4 exp2 pairs, how many run on the FMA pipe (0..4)
 constexpr float kLazyLimit = 8.0f;  // the accumulator reference moves only when a row max grew by > 2^8
 
 struct AttnArgs {
   int T;          // tokens per image
   int H;          // heads
-  int n_sub;      // 64-key steps
+  int n_sub;      // 64-key steps per item
+  int n_qt;       // query tiles per (image, head)
+  int n_items;    // n_qt * B * H
   float scale_log2;
   const __nv_bfloat16* qkv;  // [B*T, 3*H*64]
   int ld;
   __nv_bfloat16* out;  // [B*T, H*64]
   int ldo;
+  int stagger;     // cycles the second CTA of each SM waits before its first step
+  int* counter;    // global work counter (zero at launch)
+  int* counter_next;  // the counter of the next launch: zeroed by this one
+  long long* dbg;  // CA_ATTN_DEBUG=1: per-CTA {cycles, smid}
 };
 
 // d = a * s + c on two packed fp32 lanes (FFMA2)
@@ -78,30 +96,54 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) 
       : "f"(a0), "f"(a1));
 }
 
+// general packed fma: d = a * b + c on two fp32 lanes
+__device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+// 2^t for two lanes on the FMA / ALU pipes instead of the MUFU (t <= ~100): round-to-nearest split t = n + f with the
+// 1.5 * 2^23 trick, cubic minimax of 2^f on [-0.5, 0.5] (max relative error 7.6e-5, far below the bf16 rounding of P),
+// then n is added into the exponent field.  The MUFU does 16 exp2 / clk / SM; this path takes the overflow.
+__device__ __forceinline__ void exp2_poly2(float& t0, float& t1) {
+  constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+  t0 = fmaxf(t0, -125.0f);
+  t1 = fmaxf(t1, -125.0f);
+  float r0, r1, n0, n1, f0, f1, p0, p1;
+  ffma2v(r0, r1, t0, t1, 1.0f, 1.0f, kMagic, kMagic);
+  ffma2v(n0, n1, r0, r1, 1.0f, 1.0f, -kMagic, -kMagic);
+  ffma2v(f0, f1, n0, n1, -1.0f, -1.0f, t0, t1);
+  ffma2v(p0, p1, f0, f1, 0.05520550534129143f, 0.05520550534129143f, 0.24261397123336792f, 0.24261397123336792f);
+  ffma2v(p0, p1, p0, p1, f0, f1, 0.6932547688484192f, 0.6932547688484192f);
+  ffma2v(p0, p1, p0, p1, f0, f1, 0.9999276995658875f, 0.9999276995658875f);
+  t0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  t1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
+
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
-  uint64_t* k_full = bars + 0;     // [4] TMA -> MMA
-  uint64_t* k_empty = bars + 4;    // [4] MMA (commit) -> TMA
-  uint64_t* v_full = bars + 8;     // [4]
-  uint64_t* v_empty = bars + 12;   // [4]
-  uint64_t* q_ready = bars + 16;   // softmax -> MMA : Q is in TMEM
-  uint64_t* s_full = bars + 17;    // [2] MMA -> softmax : S_i is in TMEM buffer i&1
-  uint64_t* p_full = bars + 19;    // [2] softmax -> MMA : P_i is in TMEM (over S_i) and O is rescaled
-  uint64_t* pv_done = bars + 21;   // [2] MMA -> softmax : P_i V_i finished (O quiescent up to step i)
-  uint64_t* o_full = bars + 23;    // MMA -> softmax : last P V finished
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* k_full = bars + 0;               // [kRing] TMA -> MMA
+  uint64_t* k_empty = bars + kRing;          // [kRing] MMA (commit) -> TMA
+  uint64_t* v_full = bars + 2 * kRing;       // [kRing]
+  uint64_t* v_empty = bars + 3 * kRing;      // [kRing]
+  uint64_t* q_ready = bars + 4 * kRing;      // [2] softmax -> MMA : Q of item k is in TMEM buffer k&1
+  uint64_t* s_full = q_ready + 2;    // [2] MMA -> softmax : S of global step g is in TMEM buffer g&1
+  uint64_t* p_full = q_ready + 4;    // [2] softmax -> MMA : P of step g is in TMEM (over S), O rescaled / handed over
+  uint64_t* pv_done = q_ready + 6;   // [2] MMA -> softmax : P V of step g finished (O quiescent up to step g)
+  uint64_t* o_full = q_ready + 8;    // MMA -> softmax : last P V of an item finished
+  uint64_t* item_full = q_ready + 9;  // [8] scheduler -> everyone : item_q[k & 7] holds the k-th item of this CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(item_full + kItemQ);
+  volatile int* item_q = reinterpret_cast<volatile int*>(item_full + kItemQ + 1);  // [8] item index or -1 (no more work)
+  static_assert((4 * kRing + 9 + kItemQ + 1) * 8 + kItemQ * 4 <= 512, "barrier block overflows its 512 bytes");
 
   const int warp = warp_id();
   const int lane = lane_id();
-  const int qt = blockIdx.x;
-  const int bh = blockIdx.y;
-  const int b = bh / p.H;
-  const int h = bh - b * p.H;
-  const int q0 = qt * kTileQ;
-  const int col_k = (p.H + h) * kHeadDim;
-  const int col_v = (2 * p.H + h) * kHeadDim;
+  const long long t_start = clock64();
   const int n_sub = p.n_sub;
 
   if (threadIdx.x == 0) {
@@ -110,19 +152,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
       __trap();
     }
     tma_prefetch_desc(&tmap_kv);
+    if (blockIdx.x == 0) *p.counter_next = 0;
     for (int s = 0; s < kRing; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
-    mbar_init(q_ready, 4);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_ready[s], 4);
       mbar_init(&s_full[s], 1);
       mbar_init(&p_full[s], 4);
       mbar_init(&pv_done[s], 1);
     }
     mbar_init(o_full, 1);
+    for (int s = 0; s < kItemQ; ++s) mbar_init(&item_full[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -131,22 +175,72 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // k-th item of this CTA (blocks until the scheduler has published it); -1 = the CTA has run out of work
+  auto read_item = [&](int k) -> int {
+    mbar_wait(&item_full[k & (kItemQ - 1)], (k / kItemQ) & 1);
+    return item_q[k & (kItemQ - 1)];
+  };
+
   if (warp == 0) {
     if (lane == 0) {
-      auto load_k = [&](int i) {
-        const int s = i & (kRing - 1);
-        mbar_wait(&k_empty[s], ((i / kRing) & 1) ^ 1u);
-        mbar_arrive_expect_tx(&k_full[s], kSubBytes);
-        tma_load_3d(smem + kSmemK + s * kSubBytes, &tmap_kv, &k_full[s], col_k, i * kSubK, b);
+      // Scheduler + TMA producer.  Items are claimed from a global counter (the two CTAs of an SM do not progress at
+      // the same rate, and neither do all SMs: a static split leaves the slowest CTA running alone at the end).
+      // Item k+2 is claimed when the K stream enters item k, so every consumer finds its item id long published.
+      int n_claimed = 0;
+      bool exhausted = false;
+      auto claim = [&]() {
+        int it = -1;
+        if (!exhausted) {
+          it = atomicAdd(p.counter, 1);
+          if (it >= p.n_items) { it = -1; exhausted = true; }
+        }
+        item_q[n_claimed & (kItemQ - 1)] = it;
+        mbar_arrive(&item_full[n_claimed & (kItemQ - 1)]);  // release: the id is visible to whoever passes the wait
+        ++n_claimed;
       };
-      load_k(0);
-      if (n_sub > 1) load_k(1);
-      for (int i = 0; i < n_sub; ++i) {
-        const int s = i & (kRing - 1);
-        mbar_wait(&v_empty[s], ((i / kRing) & 1) ^ 1u);
+      claim();
+      claim();
+      int k_item = 0, k_step = 0, k_id = item_q[0], kg = 0;  // K stream cursor: item, step, item id, global step
+      int v_item = 0, v_step = 0, v_id = k_id, vg = 0;       // V stream cursor
+      int k_b = 0, k_col = 0, v_b = 0, v_col = 0;            // image and column of the cursor's item
+      auto load_k = [&]() {  // one K step (no-op once the K stream has run out of items)
+        if (k_id < 0) return;
+        if (k_step == 0) {
+          claim();  // entering item k_item: claim item k_item + 2
+          const int bh = k_id / p.n_qt;
+          k_b = bh / p.H;
+          k_col = (p.H + bh - k_b * p.H) * kHeadDim;
+        }
+        const int s = kg % kRing;
+        mbar_wait(&k_empty[s], ((kg / kRing) & 1) ^ 1u);
+        mbar_arrive_expect_tx(&k_full[s], kSubBytes);
+        tma_load_3d(smem + kSmemK + s * kSubBytes, &tmap_kv, &k_full[s], k_col, k_step * kSubK, k_b);
+        ++kg;
+        if (++k_step == n_sub) {
+          k_step = 0;
+          ++k_item;
+          k_id = item_q[k_item & (kItemQ - 1)];  // written by this thread
+        }
+      };
+      load_k();
+      load_k();
+      while (v_id >= 0) {
+        if (v_step == 0) {
+          const int bh = v_id / p.n_qt;
+          v_b = bh / p.H;
+          v_col = (2 * p.H + bh - v_b * p.H) * kHeadDim;
+        }
+        const int s = vg % kRing;
+        mbar_wait(&v_empty[s], ((vg / kRing) & 1) ^ 1u);
         mbar_arrive_expect_tx(&v_full[s], kSubBytes);
-        tma_load_3d(smem + kSmemV + s * kSubBytes, &tmap_kv, &v_full[s], col_v, i * kSubK, b);
-        if (i + 2 < n_sub) load_k(i + 2);
+        tma_load_3d(smem + kSmemV + s * kSubBytes, &tmap_kv, &v_full[s], v_col, v_step * kSubK, v_b);
+        ++vg;
+        if (++v_step == n_sub) {
+          v_step = 0;
+          ++v_item;
+          v_id = item_q[v_item & (kItemQ - 1)];
+        }
+        load_k();
       }
     }
   } else if (warp == 1) {
@@ -156,83 +250,140 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
     const uint64_t kd0 = umma_smem_desc_sw128(smem_u32(smem + kSmemK));
     const uint64_t vd0 = umma_smem_desc_sw128(smem_u32(smem + kSmemV), 1024, 1024);
     constexpr uint64_t kSubStep = kSubBytes >> 4;  // descriptor address units are 16 bytes
-    const uint32_t t_q = tmem_base + kTmemQ;
-    auto issue_s = [&](int i) {
-      const int s = i & (kRing - 1);
-      mbar_wait(&k_full[s], (i / kRing) & 1);
+    int s_item = 0, s_step = 0, sg = 0;  // (item, step, global step) of the next S to issue
+    bool s_more = true;
+    auto issue_s = [&]() {
+      if (!s_more) return;
+      if (s_step == 0) {  // first S of an item: the item must exist and its Q tile must be in TMEM
+        if (read_item(s_item) < 0) { s_more = false; return; }
+        mbar_wait(&q_ready[s_item & 1], (s_item >> 1) & 1);
+      }
+      const int s = sg % kRing;
+      mbar_wait(&k_full[s], (sg / kRing) & 1);
       tc_fence_after();
       if (elect_one_sync()) {
         const uint64_t kd = kd0 + s * kSubStep;
-        const uint32_t d = tmem_base + kTmemS + (i & 1) * kSubK;
+        const uint32_t d = tmem_base + kTmemS + (sg & 1) * kSubK;
+        const uint32_t t_q = tmem_base + kTmemQ + (s_item & 1) * 32;
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k) umma_bf16_ts(d, t_q + 8 * k, kd + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[i & 1]);
+        umma_commit(&s_full[sg & 1]);
         umma_commit(&k_empty[s]);
       }
       __syncwarp();
+      ++sg;
+      if (++s_step == n_sub) { s_step = 0; ++s_item; }
     };
-    mbar_wait(q_ready, 0);
-    issue_s(0);
-    if (n_sub > 1) issue_s(1);
-    for (int i = 0; i < n_sub; ++i) {
-      const int bb = i & 1;
-      const int s = i & (kRing - 1);
-      mbar_wait(&v_full[s], (i / kRing) & 1);
-      mbar_wait(&p_full[bb], (i >> 1) & 1);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint64_t vd = vd0 + s * kSubStep;
-        const uint32_t t_p = tmem_base + kTmemS + bb * kSubK;
+    issue_s();
+    issue_s();
+    int g = 0;
+    for (int k = 0; read_item(k) >= 0; ++k) {
+      for (int i = 0; i < n_sub; ++i, ++g) {
+        const int bb = g & 1;
+        const int s = g % kRing;
+        mbar_wait(&v_full[s], (g / kRing) & 1);
+        mbar_wait(&p_full[bb], (g >> 1) & 1);  // on step 0 of an item this also hands O over (previous item read out)
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t vd = vd0 + s * kSubStep;
+          const uint32_t t_p = tmem_base + kTmemS + bb * kSubK;
 #pragma unroll
-        for (int k = 0; k < kSubK / 16; ++k) {
-          // P: 16 keys = 8 packed columns; V: 16 keys = 16 rows of 128 B = 2048 B further down
-          umma_bf16_ts(tmem_base + kTmemO, t_p + 8 * k, vd + k * (2048 >> 4), idesc_o, (i | k) != 0);
+          for (int kk = 0; kk < kSubK / 16; ++kk) {
+            // P: 16 keys = 8 packed columns; V: 16 keys = 16 rows of 128 B = 2048 B further down
+            umma_bf16_ts(tmem_base + kTmemO, t_p + 8 * kk, vd + kk * (2048 >> 4), idesc_o, (i | kk) != 0);
+          }
+          umma_commit(&pv_done[bb]);
+          umma_commit(&v_empty[s]);
+          if (i == n_sub - 1) umma_commit(o_full);
         }
-        umma_commit(&pv_done[bb]);
-        umma_commit(&v_empty[s]);
-        if (i == n_sub - 1) umma_commit(o_full);
+        __syncwarp();
+        issue_s();  // S of step g+2: overwrites S_g / P_g, ordered behind PV_g by the in-order tensor pipe
       }
-      __syncwarp();
-      if (i + 2 < n_sub) issue_s(i + 2);  // overwrites S_i / P_i: ordered behind PV_i by the in-order tensor pipe
     }
   } else {
     const int quad = warp & 3;
     const int r = quad * 32 + lane;  // query row inside the tile == TMEM lane
-    const int q = q0 + r;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const uint32_t t_o = t_lane + kTmemO;
     const float scale = p.scale_log2;
-    // ---- Q row: global -> registers -> TMEM (bf16x2 per column); rows past the end of the image are zero ----
-    {
-      uint32_t qv[32];
-      if (q < p.T) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.qkv + (static_cast<size_t>(b) * p.T + q) * p.ld + h * kHeadDim);
+    // Q row of an item: global -> registers (rows past the end of the image are zero)
+    auto q_load = [&](int it, uint32_t (&qv)[32]) {
+      const int bh = it / p.n_qt;
+      const int q = (it - bh * p.n_qt) * kTileQ + r;
+      const int b = bh / p.H;
+      const int h = bh - b * p.H;
+      const bool in_range = q < p.T;
+      const uint4* src = reinterpret_cast<const uint4*>(p.qkv + (static_cast<size_t>(b) * p.T + q) * p.ld + h * kHeadDim);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const uint4 w = __ldg(src + t);
-          qv[4 * t + 0] = w.x;
-          qv[4 * t + 1] = w.y;
-          qv[4 * t + 2] = w.z;
-          qv[4 * t + 3] = w.w;
-        }
-      } else {
-#pragma unroll
-        for (int t = 0; t < 32; ++t) qv[t] = 0u;
+      for (int t = 0; t < 8; ++t) {
+        const uint4 w = in_range ? __ldg(src + t) : make_uint4(0u, 0u, 0u, 0u);
+        qv[4 * t + 0] = w.x;
+        qv[4 * t + 1] = w.y;
+        qv[4 * t + 2] = w.z;
+        qv[4 * t + 3] = w.w;
       }
+    };
+    // epilogue of the k-th item (global item index `it`): O / l -> bf16 -> global (token-major, head h at [64h, 64h+64))
+    auto epilogue = [&](int k, int it, float l) {
+      const int bh = it / p.n_qt;
+      const int q = (it - bh * p.n_qt) * kTileQ + r;
+      const int b = bh / p.H;
+      const int h = bh - b * p.H;
+      mbar_wait(o_full, k & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * p.T + q) * p.ldo + h * kHeadDim;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(t_o + c * 32, o);
+        tmem_ld_wait();
+        if (q < p.T) {
+          uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[8 * t + 0]) * inv, __uint_as_float(o[8 * t + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(o[8 * t + 2]) * inv, __uint_as_float(o[8 * t + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(o[8 * t + 4]) * inv, __uint_as_float(o[8 * t + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(o[8 * t + 6]) * inv, __uint_as_float(o[8 * t + 7]) * inv);
+            o4[t] = w;
+          }
+        }
+      }
+    };
+    if (p.stagger > 0 && blockIdx.x >= gridDim.x / 2) {  // de-phase the two CTAs of an SM
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.stagger) {}
+    }
+    int it_cur = read_item(0), it_prev = -1, it_next = -1;
+    if (it_cur >= 0) {  // Q of the first item
+      uint32_t qv[32];
+      q_load(it_cur, qv);
       tmem_st32(t_lane + kTmemQ, qv);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(q_ready);
+      if (lane == 0) mbar_arrive(&q_ready[0]);
     }
-    float m_acc = -INFINITY;  // reference (log2 domain) the O accumulator and l_run are expressed in
-    float l_run = 0.f;
-    for (int i = 0; i < n_sub; ++i) {
-      const int bb = i & 1;
+    float l_prev = 1.f;
+    int g = 0;
+    int k = 0;
+    float m_acc = -INFINITY, l_run = 0.f;  // reference (log2 domain) O and l_run are expressed in; running row sum
+    // One 64-key step.  kBoundary = step 0 of an item, which also carries the previous item's epilogue and the next
+    // item's Q tile; it is a separate instantiation so that the steady-state step stays lean.
+    auto step = [&](auto boundary_tag, const int i) {
+      constexpr bool boundary = decltype(boundary_tag)::value;
+      const int bb = g & 1;
       const int valid = p.T - i * kSubK;  // >= 64 on every step but the last
       const uint32_t t_s = t_lane + kTmemS + bb * kSubK;
+      uint32_t qv[boundary ? 32 : 1];
+      if constexpr (boundary) {
+        it_next = read_item(k + 1);
+        if (it_next >= 0) q_load(it_next, qv);  // in flight under this step's exponentials
+      }
       uint32_t v[64];
-      mbar_wait(&s_full[bb], (i >> 1) & 1);
+      mbar_wait(&s_full[bb], (g >> 1) & 1);
       tc_fence_after();
       {
         uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
@@ -259,14 +410,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
         }
       }
       const float tile_max = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale;  // scale > 0
-      // ---- lazy reference update (warp-uniform decision; always taken on the first step) ----
+      // ---- lazy reference update (warp-uniform decision; always taken on the first step of an item) ----
       if (__any_sync(0xffffffffu, tile_max > m_acc + kLazyLimit)) {
         const float m_new = fmaxf(m_acc, tile_max);
         const float alpha = fast_exp2(m_acc - m_new);  // 0 on the first step (m_acc = -inf)
         l_run *= alpha;
         m_acc = m_new;
-        if (i > 0) {
-          mbar_wait(&pv_done[bb ^ 1], ((i - 1) >> 1) & 1);  // P_{i-1} V_{i-1} (hence every earlier one) has finished
+        if (!boundary) {
+          mbar_wait(&pv_done[bb ^ 1], ((g - 1) >> 1) & 1);  // P V of step g-1 (hence every earlier one) has finished
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
@@ -274,7 +425,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
             tmem_ld16(t_o + c * 16, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+            for (int kk = 0; kk < 16; ++kk) o[kk] = __float_as_uint(__uint_as_float(o[kk]) * alpha);
             tmem_st16(t_o + c * 16, o);
           }
         }
@@ -287,10 +438,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
       for (int t = 0; t < kSubK / 8; ++t) {
         float e[8];
 #pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-          ffma2(e[k], e[k + 1], __uint_as_float(v[8 * t + k]), __uint_as_float(v[8 * t + k + 1]), scale, neg_m);
-          e[k] = fast_exp2(e[k]);
-          e[k + 1] = fast_exp2(e[k + 1]);
+        for (int kk = 0; kk < 8; kk += 2) {
+          ffma2(e[kk], e[kk + 1], __uint_as_float(v[8 * t + kk]), __uint_as_float(v[8 * t + kk + 1]), scale, neg_m);
+          if (kk >= 8 - 2 * kPolyPairs) {  // compile-time split between the MUFU and the polynomial path
+            exp2_poly2(e[kk], e[kk + 1]);
+          } else {
+            e[kk] = fast_exp2(e[kk]);
+            e[kk + 1] = fast_exp2(e[kk + 1]);
+          }
         }
         fadd2(s0, s1, e[0], e[1]);
         fadd2(s2, s3, e[2], e[3]);
@@ -303,39 +458,44 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
       }
       tmem_st32(t_s, pk);
       l_run += (s0 + s1) + (s2 + s3);
+      if constexpr (boundary) {
+        // the previous item's last P V has long finished: read its O out before this step's P V may overwrite it
+        if (k > 0) epilogue(k - 1, it_prev, l_prev);
+        if (it_next >= 0) {  // Q of the next item (its buffer was last read by item k-1, which is complete)
+          tmem_st32(t_lane + kTmemQ + ((k + 1) & 1) * 32, qv);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&q_ready[(k + 1) & 1]);
+        }
+      }
       tmem_st_wait();     // P (and a rescaled O) are in TMEM
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[bb]);
+      ++g;
+    };
+    while (it_cur >= 0) {
+      m_acc = -INFINITY;
+      l_run = 0.f;
+      step(std::true_type{}, 0);
+      for (int i = 1; i < n_sub; ++i) step(std::false_type{}, i);
+      l_prev = l_run;
+      it_prev = it_cur;
+      it_cur = it_next;
+      ++k;
     }
-    // ---- epilogue: O / l -> bf16 -> global ----
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const float inv = 1.0f / l_run;
-    __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * p.T + q) * p.ldo + h * kHeadDim;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld32(t_o + c * 32, o);
-      tmem_ld_wait();
-      if (q < p.T) {
-        uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[8 * t + 0]) * inv, __uint_as_float(o[8 * t + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(o[8 * t + 2]) * inv, __uint_as_float(o[8 * t + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(o[8 * t + 4]) * inv, __uint_as_float(o[8 * t + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(o[8 * t + 6]) * inv, __uint_as_float(o[8 * t + 7]) * inv);
-          o4[t] = w;
-        }
-      }
-      __syncwarp();
-    }
+    if (k > 0) epilogue(k - 1, it_prev, l_prev);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.dbg[2 * blockIdx.x] = clock64() - t_start;
+    p.dbg[2 * blockIdx.x + 1] = smid;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -359,14 +519,53 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
   a.T = T;
   a.H = H;
   a.n_sub = (T + kSubK - 1) / kSubK;
+  a.n_qt = (T + kTileQ - 1) / kTileQ;
+  a.n_items = a.n_qt * B * H;
   a.scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
   a.qkv = qkv;
   a.ld = ld;
   a.out = out;
   a.ldo = H * kHeadDim;
-  dim3 grid((T + kTileQ - 1) / kTileQ, B * H);
+  const int grid = a.n_items < 2 * sm_count() ? a.n_items : 2 * sm_count();  // persistent: two CTAs per SM
+  // work counter: two slots used alternately, each launch zeroes the slot of the NEXT launch (calls into this
+  // library are serialised on one stream per device, see include/cogaim_b200.h)
+  static int* d_counter = nullptr;
+  static unsigned launches = 0;
+  if (!d_counter) {
+    CA_CUDA(cudaMalloc(&d_counter, 2 * sizeof(int)));
+    CA_CUDA(cudaMemsetAsync(d_counter, 0, 2 * sizeof(int), stream));
+  }
+  a.counter = d_counter + (launches & 1);
+  a.counter_next = d_counter + ((launches + 1) & 1);
+  ++launches;
+  static const int stagger = getenv("CA_ATTN_STAGGER") ? atoi(getenv("CA_ATTN_STAGGER")) : 0;
+  a.stagger = stagger;
+  static const bool want_dbg = getenv("CA_ATTN_DEBUG") != nullptr;
+  static long long* d_dbg = nullptr;
+  a.dbg = nullptr;
+  if (want_dbg) {
+    if (!d_dbg) CA_CUDA(cudaMalloc(&d_dbg, 2 * 1024 * sizeof(long long)));
+    a.dbg = d_dbg;
+  }
   attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tm_kv, a);
   CA_CUDA(cudaGetLastError());
+  if (want_dbg) {
+    static int calls = 0;
+    if (++calls == 5) {
+      static long long h[2 * 1024];
+      CA_CUDA(cudaStreamSynchronize(stream));
+      CA_CUDA(cudaMemcpy(h, d_dbg, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost));
+      long long mn = h[0], mx = h[0];
+      double sum = 0;
+      for (int i = 0; i < grid; ++i) {
+        mn = h[2 * i] < mn ? h[2 * i] : mn;
+        mx = h[2 * i] > mx ? h[2 * i] : mx;
+        sum += h[2 * i];
+      }
+      fprintf(stderr, "[attn dbg] grid %d cycles/CTA min %lld mean %.0f max %lld\n", grid, mn, sum / grid, mx);
+      for (int i = 0; i < grid; i += 16) fprintf(stderr, "  cta %3d sm %3lld cycles %lld\n", i, h[2 * i + 1], h[2 * i]);
+    }
+  }
   return 0;
 }
 
