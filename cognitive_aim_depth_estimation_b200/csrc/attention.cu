@@ -78,33 +78,6 @@ struct AttnArgs {
   long long* dbg;  // CA_ATTN_DEBUG=1: per-CTA {cycles, smid}
 };
 
-// d = a * s + c on two packed fp32 lanes (FFMA2)
-__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float s, float c) {
-  asm("{\n\t.reg .b64 ra, rs, rc, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rs, {%4, %4};\n\tmov.b64 rc, {%5, %5};\n\t"
-      "fma.rn.f32x2 rd, ra, rs, rc;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(s), "f"(c));
-}
-__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {
-  asm("{\n\t.reg .b64 ra, rd;\n\t"
-      "mov.b64 rd, {%0, %1};\n\tmov.b64 ra, {%2, %3};\n\t"
-      "add.rn.f32x2 rd, rd, ra;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t}"
-      : "+f"(d0), "+f"(d1)
-      : "f"(a0), "f"(a1));
-}
-
-// general packed fma: d = a * b + c on two fp32 lanes
-__device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
-}
 // 2^t for two lanes on the FMA / ALU pipes instead of the MUFU (t <= ~100): round-to-nearest split t = n + f with the
 // 1.5 * 2^23 trick, cubic minimax of 2^f on [-0.5, 0.5] (max relative error 7.6e-5, far below the bf16 rounding of P),
 // then n is added into the exponent field.  The MUFU does 16 exp2 / clk / SM; this path takes the overflow.

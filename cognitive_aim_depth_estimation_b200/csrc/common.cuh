@@ -67,6 +67,52 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2): half the issue slots of the scalar forms
+// ---------------------------------------------------------------------------------------------
+// d = a * s + c with scalar s, c broadcast to both lanes
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float s, float c) {
+  asm("{\n\t.reg .b64 ra, rs, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rs, {%4, %4};\n\tmov.b64 rc, {%5, %5};\n\t"
+      "fma.rn.f32x2 rd, ra, rs, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(s), "f"(c));
+}
+// d = a * b + c, all operands per lane
+__device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+// d += a
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {
+  asm("{\n\t.reg .b64 ra, rd;\n\t"
+      "mov.b64 rd, {%0, %1};\n\tmov.b64 ra, {%2, %3};\n\t"
+      "add.rn.f32x2 rd, rd, ra;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1));
+}
+// d = a * b
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// clamp(a * b + c, 0, 1) in one FFMA.SAT
+__device__ __forceinline__ float ffma_sat(float a, float b, float c) {
+  float d;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -132,6 +178,24 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// smem tile -> global, element-wise fp32 ADD performed by the L2 (no read of the destination into the SM).
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest `kPending` bulk groups of this thread have finished READING their smem source
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -67,37 +67,31 @@ struct GemmKernelArgs {
   int dbg;  // CA_GEMM_DEBUG experiments (bit 0: skip B loads, bit 1: skip A loads) — results are then garbage
 };
 
-// Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)) = relu(x) - |x| * erfc(|x| / sqrt 2) / 2, with erfc from Abramowitz &
-// Stegun 7.1.26 (|abs err| <= 1.5e-7 on erf, 4e-7 on GELU: three orders below the bf16 rounding of the output).
-// 2 MUFU (rcp, ex2) + 11 FMA-pipe ops, branch-free; the negative tail is evaluated directly (no cancellation).
-// w = |x| * sqrt(log2(e) / 2) so that exp(-z^2) = 2^(-w^2); the 1/2 is folded into the polynomial coefficients.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float ax = fabsf(x);
-  const float w = ax * 0.84932180028801904f;
-  const float t = __fdividef(1.0f, fmaf(0.27273784f, w, 1.0f));  // 1 / (1 + 0.3275911 z)
-  float poly = fmaf(0.5307027145f, t, -0.7265760135f);
-  poly = fmaf(poly, t, 0.7107068705f);
-  poly = fmaf(poly, t, -0.142248368f);
-  poly = fmaf(poly, t, 0.127414796f);
-  const float half_erfc = poly * t * fast_exp2(-w * w);
-  return fmaf(-ax, half_erfc, fmaxf(x, 0.f));
-}
-
-// Residual loads of one 32-column chunk for this lane's (8 rows x 16 B) slots; rows past M are skipped.
-__device__ __forceinline__ void resid_load_chunk(const GemmKernelArgs& p, const float* xchunk, int mt, int quad,
-                                                 int lrow, float4 (&dst)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int grow = mt * BM + quad * 32 + lrow + 4 * i;
-    if (grow < p.M && !(p.dbg & 4)) dst[i] = *reinterpret_cast<const float4*>(xchunk + static_cast<size_t>(grow) * p.ldo);
-  }
+// erf-GELU of two values, x * Phi(x), without the MUFU: Phi(x) - 1/2 is an odd degree-17 minimax polynomial on
+// |x| <= 4.2 whose leading coefficient is positive, so one saturating FMA (FFMA.SAT clamps to [0, 1]) both adds the 1/2
+// and supplies the exact limits beyond the fit range.  |Phi error| <= 1.3e-5 and |GELU error| <= 5.5e-5 for EVERY x
+// (checked in fp32 Horner arithmetic over [-12, 12], tests/test_gemm_gpu.py), one to two orders below the bf16 rounding
+// of the output.  8 FFMA2 + 2 FMUL2 per pair + 1 FFMA.SAT per value: 7 issue slots per value against ~20 for an
+// exp/rcp formulation whose 2 MUFU per value alone would need 4096 clk of a 6144-clk 128 x 256 x 768 tile.
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  float s0, s1, p0, p1;
+  fmul2(s0, s1, x0, x1, x0, x1);
+  ffma2(p0, p1, s0, s1, 6.013480685629347e-11f, -5.644098521884189e-09f);
+  ffma2v(p0, p1, p0, p1, s0, s1, 2.3467518417419342e-07f, 2.3467518417419342e-07f);
+  ffma2v(p0, p1, p0, p1, s0, s1, -5.765378773503471e-06f, -5.765378773503471e-06f);
+  ffma2v(p0, p1, p0, p1, s0, s1, 9.46131840464659e-05f, 9.46131840464659e-05f);
+  ffma2v(p0, p1, p0, p1, s0, s1, -0.0011143309529870749f, -0.0011143309529870749f);
+  ffma2v(p0, p1, p0, p1, s0, s1, 0.009830592200160027f, 0.009830592200160027f);
+  ffma2v(p0, p1, p0, p1, s0, s1, -0.06636093556880951f, -0.06636093556880951f);
+  ffma2v(p0, p1, p0, p1, s0, s1, 0.39890772104263306f, 0.39890772104263306f);
+  const float phi0 = ffma_sat(p0, x0, 0.5f), phi1 = ffma_sat(p1, x1, 0.5f);
+  fmul2(x0, x1, x0, x1, phi0, phi1);
 }
 
 // One epilogue warp: rows [32*q, 32*q+32) of the tile (q = warp_id % 4), columns [col0, col0 + BN/2).
 template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, uint32_t tmem_acc, int b, int mt, int nt,
-                                              int quad, int half, uint8_t* stage,
-                                              float4 (&xr)[2][8]) {
+__device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUtensorMap* tmap_x, uint32_t tmem_acc, int b,
+                                              int mt, int nt, int quad, int half, uint8_t* stage) {
   constexpr int kSpan = BN / 2;
   const int lane = lane_id();
   const int row = mt * BM + quad * 32 + lane;           // row inside batch b
@@ -191,7 +185,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, uint32_t 
               }
               if constexpr (EPI == EPI_GELU_BF16) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = gelu_erf(a[i]);
+                for (int i = 0; i < 8; i += 2) gelu_erf2(a[i], a[i + 1]);
               }
               uint4 w;
               w.x = pack_bf16x2(a[0], a[1]);
@@ -217,43 +211,35 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, uint32_t 
         }
       }
     } else if constexpr (EPI == EPI_RESID_F32) {
-      // x += ls * (acc + bias), in place.  The residual reads are the only long-latency operation of this epilogue
-      // (x does not fit L2 between layers), so they are software-pipelined one 32-column chunk ahead, and chunk 0 was
-      // issued by resid_load_chunk() BEFORE the wait on the accumulator, i.e. it overlaps the tile's own MMAs.
-      float* xbase = reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride + col_base + seg * 4;
+      // x += ls * (acc + bias), in place, WITHOUT reading x into the SM: each 32-row x 32-column piece is finished in
+      // registers, laid out in the warp's 128B-swizzled staging buffer and handed to the TMA as a reduce-add
+      // (cp.reduce.async.bulk.tensor .add, fp32): the L2 performs the read-modify-write.  x does not fit L2 between
+      // layers, so a load-modify-store epilogue is bound by the latency of its residual reads (8 warps x 4 KB in
+      // flight per SM); the reduce form only ever writes.  Rows past M are clipped by the tensor map.
       constexpr int kChunks = kSpan / 32;
-#pragma unroll
+#pragma unroll 1
       for (int g = 0; g < kChunks; ++g) {
-        if (g + 1 < kChunks) resid_load_chunk(p, xbase + (g + 1) * 32, mt, quad, lrow, xr[(g + 1) & 1]);
         const int c = g * 32;
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
         const int col = col_base + c;
+        if (lane == 0) bulk_wait_group_read<0>();  // the previous reduce has finished reading the staging buffer
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+          const float4 l4 = __ldg(reinterpret_cast<const float4*>(p.ls + col) + j);
           *reinterpret_cast<float4*>(stage + epi_off(lane, j)) =
-              make_float4(__uint_as_float(v[4 * j + 0]) + t.x, __uint_as_float(v[4 * j + 1]) + t.y,
-                          __uint_as_float(v[4 * j + 2]) + t.z, __uint_as_float(v[4 * j + 3]) + t.w);
+              make_float4(l4.x * (__uint_as_float(v[4 * j + 0]) + t.x), l4.y * (__uint_as_float(v[4 * j + 1]) + t.y),
+                          l4.z * (__uint_as_float(v[4 * j + 2]) + t.z), l4.w * (__uint_as_float(v[4 * j + 3]) + t.w));
         }
+        fence_proxy_async_smem();
         __syncwarp();
-        const float4 l4 = __ldg(reinterpret_cast<const float4*>(p.ls + col) + seg);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = lrow + 4 * i;
-          const int grow = mt * BM + quad * 32 + rr;
-          const float4 a = *reinterpret_cast<const float4*>(stage + epi_off(rr, seg));
-          if (grow < p.M && !(p.dbg & 8)) {
-            float4 x = xr[g & 1][i];
-            x.x = fmaf(l4.x, a.x, x.x);
-            x.y = fmaf(l4.y, a.y, x.y);
-            x.z = fmaf(l4.z, a.z, x.z);
-            x.w = fmaf(l4.w, a.w, x.w);
-            *reinterpret_cast<float4*>(xbase + static_cast<size_t>(grow) * p.ldo + c) = x;
-          }
+        if (lane == 0) {
+          tma_reduce_add_2d(tmap_x, stage, col, mt * BM + quad * 32);
+          bulk_commit_group();
         }
-        __syncwarp();
       }
     } else {
 #pragma unroll 1
@@ -305,7 +291,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, uint32_t 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)  // 10 warps -> 3 warps on two SMSPs -> 168 registers per thread
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                    const GemmKernelArgs p) {
+                    const __grid_constant__ CUtensorMap tmap_x, const GemmKernelArgs p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms are 1024 B; align the ring explicitly (dynamic smem is only 16 B aligned by contract).
@@ -410,21 +396,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int rest = tile / p.n_tiles;
       const int mt = rest % p.m_tiles;
       const int b = rest / p.m_tiles;
-      float4 xr[2][8];
-      if constexpr (EPI == EPI_RESID_F32) {  // first residual chunk: issued before the accumulator is ready
-        const float* xbase = reinterpret_cast<const float*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride +
-                             nt * BN + half * (BN / 2) + (lane & 7) * 4;
-        resid_load_chunk(p, xbase, mt, quad, lane >> 3, xr[0]);
-      }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN, EPI>(p, tmem_base + static_cast<uint32_t>(acc * BN), b, mt, nt, quad, half,
-                             smem_stage + e * kEpiStageBytes, xr);
+      epilogue_tile<BN, EPI>(p, &tmap_x, tmem_base + static_cast<uint32_t>(acc * BN), b, mt, nt, quad, half,
+                             smem_stage + e * kEpiStageBytes);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+    }
+    if constexpr (EPI == EPI_RESID_F32) {
+      if (lane == 0) bulk_wait_group<0>();  // every reduce of this warp has been performed
     }
   }
 
@@ -437,7 +420,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 template <int BN, int EPI>
-int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmKernelArgs& ka, cudaStream_t stream) {
+int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tx, const GemmKernelArgs& ka,
+                cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tcgen05_kernel<BN, EPI>;
   static bool configured = false;  // per instantiation
@@ -446,7 +430,7 @@ int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmKernelAr
     configured = true;
   }
   int grid = ka.total_tiles < sm_count() ? ka.total_tiles : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, ka);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, tx, ka);
   CA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -486,6 +470,13 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   CA_REQUIRE(wbs % 8 == 0, "gemm: W batch stride must be a multiple of 8 elements");
   CA_TRY(make_tmap_3d(&tw, a.W, wb ? a.batch : 1, a.N, a.K, a.ldw, wbs, bn));
 
+  CUtensorMap tx = ta;  // only the residual epilogue reads it
+  if (a.epilogue == EPI_RESID_F32) {
+    CA_REQUIRE(a.batch == 1, "gemm: the residual epilogue is not batched");
+    CA_REQUIRE(a.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0, "gemm: residual rows must be 16-byte aligned");
+    CA_TRY(make_tmap_f32_2d(&tx, a.out, a.M, a.N, a.ldo, 32));
+  }
+
   GemmKernelArgs ka;
   ka.M = a.M;
   ka.N = a.N;
@@ -511,13 +502,13 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   ka.dbg = dbg;
 
   switch (a.epilogue) {
-    case EPI_BIAS_BF16: return launch_inst<256, EPI_BIAS_BF16>(ta, tw, ka, stream);
-    case EPI_GELU_BF16: return launch_inst<256, EPI_GELU_BF16>(ta, tw, ka, stream);
-    case EPI_RESID_F32: return launch_inst<256, EPI_RESID_F32>(ta, tw, ka, stream);
-    case EPI_PATCH_F32: return launch_inst<256, EPI_PATCH_F32>(ta, tw, ka, stream);
-    case EPI_F32: return launch_inst<256, EPI_F32>(ta, tw, ka, stream);
-    case EPI_ROWSTATS: return launch_inst<128, EPI_ROWSTATS>(ta, tw, ka, stream);
-    case EPI_COLSUM: return launch_inst<128, EPI_COLSUM>(ta, tw, ka, stream);
+    case EPI_BIAS_BF16: return launch_inst<256, EPI_BIAS_BF16>(ta, tw, tx, ka, stream);
+    case EPI_GELU_BF16: return launch_inst<256, EPI_GELU_BF16>(ta, tw, tx, ka, stream);
+    case EPI_RESID_F32: return launch_inst<256, EPI_RESID_F32>(ta, tw, tx, ka, stream);
+    case EPI_PATCH_F32: return launch_inst<256, EPI_PATCH_F32>(ta, tw, tx, ka, stream);
+    case EPI_F32: return launch_inst<256, EPI_F32>(ta, tw, tx, ka, stream);
+    case EPI_ROWSTATS: return launch_inst<128, EPI_ROWSTATS>(ta, tw, tx, ka, stream);
+    case EPI_COLSUM: return launch_inst<128, EPI_COLSUM>(ta, tw, tx, ka, stream);
     default: return invalid("gemm: unknown epilogue");
   }
 }

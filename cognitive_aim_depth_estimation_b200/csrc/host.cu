@@ -42,8 +42,23 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int make_tmap_sw128(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box);
+
 int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap_sw128(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  uint64_t dims[2] = {cols, rows};
+  uint64_t strides[1] = {ld * 4};
+  uint32_t box[2] = {32, box_rows};
+  return make_tmap_sw128(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, 2, dims, strides, box);
+}
+
+static int make_tmap_sw128(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver / GPU?)");
@@ -63,7 +78,7 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uin
       gstr[i - 1] = strides_bytes[i - 1];
     }
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+  CUresult r = fn(out, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
                   gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -41,6 +41,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint64_t batch_stride, uint32_t box_rows);
 
+// Row-major [rows, cols] fp32 matrix, 128B swizzle, box = [box_rows, 32 columns (128 bytes)] — the destination of the
+// residual epilogue's TMA reduce-add.
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
 int sm_count();
 
 }  // namespace ca

@@ -44,6 +44,27 @@ def test_gemm_bias_bf16_and_gelu(cuda_device):
     assert _relerr(out, torch.nn.functional.gelu(ref)) < 4e-3
 
 
+def test_gelu_epilogue_pointwise_accuracy(cuda_device):
+    """The MUFU-free erf-GELU of the fc1 epilogue (odd minimax polynomial + saturating FMA) against torch's erf GELU on
+    a dense sweep of pre-activations in [-12, 12]: the pre-activation is delivered exactly through the bias of a
+    zero-weight GEMM, so the only error measured is the GELU approximation plus the bf16 rounding of the output."""
+    from cognitive_aim_depth_estimation_b200 import ops
+    M, N, K = 128, 3072, 64
+    A = torch.zeros((M, K), device=cuda_device, dtype=torch.bfloat16)
+    W = torch.zeros((N, K), device=cuda_device, dtype=torch.bfloat16)
+    for lo, hi in ((-12.0, 12.0), (-5.0, 5.0), (-1.0, 1.0), (-0.01, 0.01)):
+        bias = torch.linspace(lo, hi, N, device=cuda_device)
+        out = torch.zeros((M, N), device=cuda_device, dtype=torch.bfloat16)
+        ops.gemm(A, W, ops.EPI_GELU_BF16, out, bias=bias)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.gelu(bias.double()).float()
+        got = out[0].float()
+        assert torch.equal(out[0], out[-1])
+        # bf16 rounding of the exact value is the floor: half an ulp = 2^-9 relative
+        err = (got - ref).abs()
+        assert (err <= ref.abs() * 2.0 ** -8 + 6e-5).all(), (err - ref.abs() * 2.0 ** -8).max()
+
+
 def test_gemm_resid_inplace(cuda_device):
     from cognitive_aim_depth_estimation_b200 import ops
     M, N, K = 1370 * 3, 768, 3072
