@@ -73,8 +73,7 @@ struct AttnArgs {
   __nv_bfloat16* out;  // [B*T, H*64]
   int ldo;
   int stagger;     // cycles the second CTA of each SM waits before its first step
-  int* counter;    // global work counter (zero at launch)
-  int* counter_next;  // the counter of the next launch: zeroed by this one
+  int* counter;    // [0] global work counter, [1] count of finished CTAs; both zero at launch, re-zeroed by the last CTA
   long long* dbg;  // CA_ATTN_DEBUG=1: per-CTA {cycles, smid}
 };
 
@@ -125,7 +124,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
       __trap();
     }
     tma_prefetch_desc(&tmap_kv);
-    if (blockIdx.x == 0) *p.counter_next = 0;
     for (int s = 0; s < kRing; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
@@ -463,6 +461,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    // The last CTA to leave re-arms the work counter for the next launch (every claim of this launch has returned by
+    // then: a CTA only gets here after its scheduler drew the out-of-work sentinel), so launches — eager or replayed
+    // from a CUDA graph — need no host-side reset.
+    __threadfence();
+    if (atomicAdd(p.counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+      p.counter[0] = 0;
+      p.counter[1] = 0;
+      __threadfence();
+    }
+  }
   if (p.dbg && threadIdx.x == 0) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -500,17 +509,17 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
   a.out = out;
   a.ldo = H * kHeadDim;
   const int grid = a.n_items < 2 * sm_count() ? a.n_items : 2 * sm_count();  // persistent: two CTAs per SM
-  // work counter: two slots used alternately, each launch zeroes the slot of the NEXT launch (calls into this
-  // library are serialised on one stream per device, see include/cogaim_b200.h)
-  static int* d_counter = nullptr;
-  static unsigned launches = 0;
-  if (!d_counter) {
-    CA_CUDA(cudaMalloc(&d_counter, 2 * sizeof(int)));
-    CA_CUDA(cudaMemsetAsync(d_counter, 0, 2 * sizeof(int), stream));
+  // work counter + exit counter, self-resetting (launches on one device are serialised on a stream, see
+  // include/cogaim_b200.h); allocated on first use, per device
+  static int* d_counter[64] = {};
+  int dev = 0;
+  CA_CUDA(cudaGetDevice(&dev));
+  CA_REQUIRE(dev >= 0 && dev < 64, "attention: device index out of range");
+  if (!d_counter[dev]) {
+    CA_CUDA(cudaMalloc(&d_counter[dev], 2 * sizeof(int)));
+    CA_CUDA(cudaMemset(d_counter[dev], 0, 2 * sizeof(int)));
   }
-  a.counter = d_counter + (launches & 1);
-  a.counter_next = d_counter + ((launches + 1) & 1);
-  ++launches;
+  a.counter = d_counter[dev];
   static const int stagger = getenv("CA_ATTN_STAGGER") ? atoi(getenv("CA_ATTN_STAGGER")) : 0;
   a.stagger = stagger;
   static const bool want_dbg = getenv("CA_ATTN_DEBUG") != nullptr;

@@ -17,6 +17,7 @@ Differences that are deliberate:
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -156,6 +157,10 @@ class CognitiveAimModel(nn.Module):
         self._ws: Dict = {}       # workspaces keyed by (B, S)
         self.validate_inputs = True
         self.rng_replay_batch = None  # sharded runs: replay the reference's RNG draws at the GLOBAL batch size
+        # The ~110 launches of one forward are captured once per (batch, resolution, path) into a CUDA graph and
+        # replayed: the launch gaps between dependent kernels (~0.4 ms of a 14 ms step) and the host-side launch work
+        # disappear.  Per-call inputs (mask, per-call projection, EXIF) are copied into fixed buffers the graph reads.
+        self.use_cuda_graphs = os.environ.get("CA_NO_GRAPHS", "0") in ("", "0")
         self.eval()
 
     # -- nn.Module protocol -----------------------------------------------------------------------------
@@ -309,6 +314,10 @@ class CognitiveAimModel(nn.Module):
                 "pooled": torch.empty(B, _D, **fl), "feats": torch.empty(B, self.cfg.num_iterations, 64, **fl),
                 "focal_feat": torch.empty(B, 64, **fl), "fused": torch.empty(B, 192, **fl),
                 "depth": torch.empty(B, **fl), "conf": torch.empty(B, **fl),
+                # per-call inputs, at fixed addresses so that captured graphs can be replayed
+                "mask_in": torch.empty(N, **fl), "tmpw": torch.empty(64, _D, **fl), "tmpb": torch.empty(64, **fl),
+                "exif_in": torch.zeros(B, 3, **fl), "cam_in": torch.zeros(B, device=dev, dtype=torch.int64),
+                "graphs": {},
             }
             if len(self._ws) >= 4:  # keep the cache bounded
                 self._ws.pop(next(iter(self._ws)))
@@ -341,6 +350,16 @@ class CognitiveAimModel(nn.Module):
         tb = self._grid_tables(g)
         if patches is None:
             patches = ops.patchify_f32(images, ws["patches"])
+        self._run(ws, ("backbone", patches.data_ptr()), lambda: self._backbone_layers(ws, patches, B, S))
+        return ws["tokens"]
+
+    def _backbone_layers(self, ws, patches, B: int, S: int):
+        """Embedding GEMM + 12 encoder layers + final LayerNorm on patch rows already in `patches` (graph-capturable:
+        fixed addresses, no host synchronisation, no allocation)."""
+        pk = self._packed
+        g = S // 14
+        N, T = g * g, g * g + 1
+        tb = self._tables[g]
         x, h = ws["x"], ws["h"]
         ops.cls_rows(x, pk["cls"], tb["pos"], B, T, _D)
         ops.gemm(patches, pk["patch_w"], ops.EPI_PATCH_F32, x, bias=pk["patch_b"], pos=tb["pos"], patches_per_img=N)
@@ -354,6 +373,28 @@ class CognitiveAimModel(nn.Module):
             ops.gemm(ws["mlp"], L["w2"], ops.EPI_RESID_F32, x, bias=L["b2"], ls=L["ls2"])
         ops.layernorm(x, pk["lnw"], pk["lnb"], ws["tokens"].view(B * T, _D))
         return ws["tokens"]
+
+    def _run(self, ws, key, fn):
+        """Run `fn` (a fixed sequence of launches on fixed buffers): eagerly, or — with `use_cuda_graphs` — captured
+        once per key and replayed.  The first call runs eagerly as well: it performs the library's one-time
+        allocations and attribute settings, which are illegal during capture."""
+        if not self.use_cuda_graphs or ops.tracing_events():
+            fn()
+            return
+        graph = ws["graphs"].get(key)
+        if graph is None:
+            fn()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                n0 = ops.launch_count()
+                fn()
+                launches = ops.launch_count() - n0
+            ws["graphs"][key] = (graph, launches)
+            if len(ws["graphs"]) > 8:
+                ws["graphs"].pop(next(iter(ws["graphs"])))
+            return  # the eager run above produced this call's results
+        graph[0].replay()
+        ops.count_launches(graph[1])
 
     def _focal_iterations(self, ws, B: int, g: int, want_features: bool):
         """IterativeFocalStream (src/model.py:391-455): per iteration Q|K projection, two tensor-core passes over
@@ -457,15 +498,27 @@ class CognitiveAimModel(nn.Module):
         tmp_w = tmp.weight.detach().to(dev, non_blocking=True)
         tmp_b = tmp.bias.detach().to(dev, non_blocking=True)
         ws = self._workspace(B, S)
-        self.backbone_tokens(images)
-        base = self._focal_iterations(ws, B, g, want_features=False)
-        ops.guided_softmax(base, mask, ws["heat"], ws["argmax"], B, N)
-        ops.weighted_pool(ws["tokens"], T * _D, 1, ws["heat"], None, ws["pool"], B, N, _D, _POOL_SPLITS)
-        ops.heads(pk["heads"], tokens=ws["tokens"], tokens_per_img=T, depth=ws["depth"], conf=ws["conf"], B=B,
-                  pool_partial=ws["pool"], pool_splits=_POOL_SPLITS, tmp_w=tmp_w, tmp_b=tmp_b,
-                  pooled_out=ws["pooled"], exif=exif, camera_idx=cam)
-        # keep the temporaries referenced until the next call (their kernels are enqueued, not finished)
-        self._keepalive = (tmp_w, tmp_b, exif, cam, mask)
+        ws["mask_in"].copy_(mask, non_blocking=True)
+        ws["tmpw"].copy_(tmp_w, non_blocking=True)
+        ws["tmpb"].copy_(tmp_b, non_blocking=True)
+        ws["exif_in"].copy_(exif, non_blocking=True)
+        ws["cam_in"].copy_(cam, non_blocking=True)
+        images = images.to(dev, torch.float32).contiguous()
+        self._grid_tables(g)
+        patches = ops.patchify_f32(images, ws["patches"])
+
+        def device_pass():
+            self._backbone_layers(ws, patches, B, S)
+            base = self._focal_iterations(ws, B, g, want_features=False)
+            ops.guided_softmax(base, ws["mask_in"], ws["heat"], ws["argmax"], B, N)
+            ops.weighted_pool(ws["tokens"], T * _D, 1, ws["heat"], None, ws["pool"], B, N, _D, _POOL_SPLITS)
+            ops.heads(pk["heads"], tokens=ws["tokens"], tokens_per_img=T, depth=ws["depth"], conf=ws["conf"], B=B,
+                      pool_partial=ws["pool"], pool_splits=_POOL_SPLITS, tmp_w=ws["tmpw"], tmp_b=ws["tmpb"],
+                      pooled_out=ws["pooled"], exif=ws["exif_in"], camera_idx=ws["cam_in"])
+
+        self._run(ws, "guided", device_pass)
+        # keep the temporaries referenced until the next call (their copies are enqueued, not finished)
+        self._keepalive = (tmp_w, tmp_b, exif, cam, mask, images)
         heat = ws["heat"].clone()
         self._last_attention_weights = heat  # :1212
         self._last_argmax = ws["argmax"].clone()
@@ -485,12 +538,24 @@ class CognitiveAimModel(nn.Module):
         exif, cam = self._exif_tensors(exif_data, B)
         self._replay_reference_rng(B)
         ws = self._workspace(B, S)
-        self.backbone_tokens(images)
-        att = self._focal_iterations(ws, B, g, want_features=True)
-        ops.heads(pk["heads"], tokens=ws["tokens"], tokens_per_img=T, depth=ws["depth"], conf=ws["conf"], B=B,
-                  focal_feat=ws["focal_feat"], exif=exif, camera_idx=cam, fused_out=ws["fused"])
-        self._keepalive = (exif, cam)
-        att = att.clone()
+        has_exif = exif is not None
+        if has_exif:
+            ws["exif_in"].copy_(exif, non_blocking=True)
+            ws["cam_in"].copy_(cam, non_blocking=True)
+        images = images.to(self._device(), torch.float32).contiguous()
+        self._grid_tables(g)
+        patches = ops.patchify_f32(images, ws["patches"])
+
+        def device_pass():
+            self._backbone_layers(ws, patches, B, S)
+            self._focal_iterations(ws, B, g, want_features=True)
+            ops.heads(pk["heads"], tokens=ws["tokens"], tokens_per_img=T, depth=ws["depth"], conf=ws["conf"], B=B,
+                      focal_feat=ws["focal_feat"], exif=ws["exif_in"] if has_exif else None,
+                      camera_idx=ws["cam_in"] if has_exif else None, fused_out=ws["fused"])
+
+        self._run(ws, ("unguided", has_exif), device_pass)
+        self._keepalive = (exif, cam, images)
+        att = ws["attn"][self.cfg.num_iterations - 1].clone()
         self.fusion_features = ws["fused"].clone()  # :1089
         if keep_last:
             if not hasattr(self, "_last_attention_weights"):  # :1093-1113 only set when absent

@@ -39,6 +39,20 @@ def trace_stop():
     return n, ev
 
 
+def tracing_events() -> bool:
+    """True while per-launch CUDA events are being recorded (graph replay would hide the launches from them)."""
+    return _Trace.events is not None
+
+
+def launch_count() -> int:
+    return _Trace.launches
+
+
+def count_launches(n: int):
+    """Account for `n` kernels launched by replaying a captured graph."""
+    _Trace.launches += n
+
+
 def _begin():
     if _Trace.events is None:
         return None
