@@ -325,6 +325,19 @@ class CognitiveAimModel(nn.Module):
         return ws
 
     # -- stages -----------------------------------------------------------------------------------------
+    def _pinned_slot(self):
+        """Next buffer of a 4-deep ring of pinned host staging areas for the per-call projection; waits (normally not
+        at all: the copy is four calls old) until the previous async copy out of it has completed."""
+        ring = getattr(self, "_pinned_ring", None)
+        if ring is None:
+            ring = {"slots": [{"w": torch.empty(64, _D).pin_memory(), "b": torch.empty(64).pin_memory(),
+                               "event": torch.cuda.Event()} for _ in range(4)], "next": 0}
+            self._pinned_ring = ring
+        slot = ring["slots"][ring["next"]]
+        ring["next"] = (ring["next"] + 1) % len(ring["slots"])
+        slot["event"].synchronize()
+        return slot
+
     @staticmethod
     def _check_images(images):
         if not torch.is_tensor(images) or images.dim() != 4 or images.shape[1] != 3:
@@ -495,12 +508,17 @@ class CognitiveAimModel(nn.Module):
         exif, cam = self._exif_tensors(exif_data, B)
         self._replay_reference_rng(B)
         tmp = nn.Linear(_D, 64)  # same constructor => same CPU-generator draws as src/model.py:1421
-        tmp_w = tmp.weight.detach().to(dev, non_blocking=True)
-        tmp_b = tmp.bias.detach().to(dev, non_blocking=True)
         ws = self._workspace(B, S)
+        # The projection travels through a small ring of PINNED staging buffers: a copy from pageable memory would block
+        # the host until the stream has drained, i.e. serialise host-side launch work with the previous step.
+        slot = self._pinned_slot()
+        slot["w"].copy_(tmp.weight.detach())
+        slot["b"].copy_(tmp.bias.detach())
         ws["mask_in"].copy_(mask, non_blocking=True)
-        ws["tmpw"].copy_(tmp_w, non_blocking=True)
-        ws["tmpb"].copy_(tmp_b, non_blocking=True)
+        ws["tmpw"].copy_(slot["w"], non_blocking=True)
+        ws["tmpb"].copy_(slot["b"], non_blocking=True)
+        slot["event"].record()
+        tmp_w = tmp_b = None
         ws["exif_in"].copy_(exif, non_blocking=True)
         ws["cam_in"].copy_(cam, non_blocking=True)
         images = images.to(dev, torch.float32).contiguous()
