@@ -1,0 +1,125 @@
+"""Full-size and scale checks of the B200 path (BASELINE.json configs 2, 4, 5): properties that do not need the CPU
+oracle at full size (batch-composition invariance, sharding invariance, graph replay == eager launch, row sums),
+plus one oracle parity case at 1036 x 1036 (4x tokens, bicubic position-embedding interpolation, ragged tiles)."""
+import pytest
+import torch
+
+from oracle import cogaim_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CFG = {"model": {"cognitive_modules": ["ambient_stream", "iterative_focal_stream", "exif_prior_database"]}}
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return orc.build_state_dict(0)
+
+
+@pytest.fixture(scope="module")
+def model(cuda_device, sd):
+    from cognitive_aim_depth_estimation_b200.model import create_model
+    m = create_model(CFG, {"num_cameras": 71}, device=cuda_device)
+    m.load_state_dict(sd)
+    return m
+
+
+def _exif(ex, lo=None, hi=None):
+    return {k: v[lo:hi].cuda() for k, v in ex.items()}
+
+
+def _guided(model, x, ex, instruction, replay_batch=None):
+    torch.manual_seed(11)
+    model.rng_replay_batch = replay_batch
+    try:
+        out = model.forward_with_guidance(x, ex, instruction, return_attention=True)
+    finally:
+        model.rng_replay_batch = None
+    return [t.clone() for t in out]
+
+
+def test_full_batch_properties_and_batch_invariance(model):
+    """Config 2 (518 x 518, 32 images / GPU): every image's outputs are bit-identical to the ones it gets in a batch of
+    2 (no kernel couples images: same tiles, same reduction order), heat-map rows sum to 1, outputs finite."""
+    B = 32
+    x = orc.synthetic_images(B, 518).cuda()
+    ex = orc.synthetic_exif(B)
+    depth, conf, heat = _guided(model, x, _exif(ex), "bottom-right")
+    assert depth.shape == (B, 1) and conf.shape == (B, 1) and heat.shape == (B, 1369)
+    assert torch.isfinite(depth).all() and torch.isfinite(conf).all() and torch.isfinite(heat).all()
+    assert (depth > 0).all() and ((conf > 0) & (conf < 1)).all()
+    assert torch.allclose(heat.sum(-1), torch.ones(B, device=heat.device), atol=1e-5)
+    for lo in (0, 14, 30):
+        d2, c2, h2 = _guided(model, x[lo:lo + 2], _exif(ex, lo, lo + 2), "bottom-right", replay_batch=B)
+        assert torch.equal(d2, depth[lo:lo + 2]) and torch.equal(c2, conf[lo:lo + 2]) and torch.equal(h2, heat[lo:lo + 2])
+
+
+def test_sharded_run_equals_unsharded(model):
+    """contiguous shards of the global batch, each run as its own call (what each rank of a torchrun
+    job does), reproduce the un-sharded result bit for bit, ragged shard included."""
+    from cognitive_aim_depth_estimation_b200.sharding import ShardedInference
+    B = 7
+    x = orc.synthetic_images(B, 224).cuda()
+    ex = _exif(orc.synthetic_exif(B))
+    want = _guided(model, x, ex, "left")
+    for world in (2, 3):
+        parts = []
+        for rank in range(world):
+            torch.manual_seed(11)
+            parts.append(ShardedInference(model, rank, world).forward_with_guidance(x, ex, "left", return_attention=True))
+        for i in range(3):
+            assert torch.equal(torch.cat([p[i] for p in parts]), want[i]), (world, i)
+
+
+def test_graph_replay_equals_eager(model):
+    """The CUDA-graph replay of the forward launches exactly the eager sequence: identical bits."""
+    x = orc.synthetic_images(3, 224).cuda()
+    ex = _exif(orc.synthetic_exif(3))
+    assert model.use_cuda_graphs
+    a = _guided(model, x, ex, "top")          # first call: eager + capture
+    b = _guided(model, x, ex, "top")          # replay
+    c = _guided(model, x, ex, "center")       # replay with another mask through the same fixed buffer
+    model.use_cuda_graphs = False
+    try:
+        d = _guided(model, x, ex, "top")
+        e = _guided(model, x, ex, "center")
+    finally:
+        model.use_cuda_graphs = True
+    for i in range(3):
+        assert torch.equal(a[i], b[i]) and torch.equal(a[i], d[i]) and torch.equal(c[i], e[i])
+    assert not torch.equal(a[2], c[2])
+    u1 = [t.clone() for t in model(x, ex, return_attention=True)]
+    u2 = [t.clone() for t in model(x, ex, return_attention=True)]
+    for i in range(3):
+        assert torch.equal(u1[i], u2[i])
+
+
+def test_high_resolution_parity(model, sd):
+    """Config 5: 1036 x 1036 (g = 74, 5477 tokens): bicubic position-embedding interpolation, 43 query tiles with a
+    ragged tail, 86 key steps; same tolerances as at 518 (depth abs-rel 1e-2, heat-map 1e-2, argmax exact)."""
+    x = orc.synthetic_images(1, 1036)
+    ex = orc.synthetic_exif(1)
+    tokens = orc.dinov2_tokens(sd, x)
+    tok = model.backbone_tokens(x.cuda()).cpu()
+    assert ((tok - tokens).norm() / tokens.norm()).item() < 1.5e-2
+    for instruction in ("center", "top-right"):
+        torch.manual_seed(11)
+        ref = orc.forward_with_guidance(sd, None, ex, instruction, tokens=tokens, update_history=False)
+        depth, conf, heat = _guided(model, x.cuda(), _exif(ex), instruction)
+        assert ((depth.cpu() - ref["depth"]).abs() / ref["depth"].abs()).max().item() <= 1e-2
+        assert (conf.cpu() - ref["confidence"]).abs().max().item() <= 1e-2
+        assert (heat.cpu() - ref["heatmap"]).abs().max().item() <= 1e-2
+        top2 = ref["heatmap"].topk(2, dim=-1).values
+        margin = ((top2[:, 0] - top2[:, 1]) / top2[:, 0]).min().item()
+        assert torch.equal(heat.cpu().argmax(-1), ref["heatmap"].argmax(-1)), f"oracle top-1/top-2 margin {margin:.2e}"
+
+
+def test_batch64_runs(model):
+    """Config 4 (64 images / GPU at 518 x 518): workspace sizing and tile counts at M = 87 680 rows."""
+    B = 64
+    x = orc.synthetic_images(B, 518, seed=77).cuda()
+    ex = _exif(orc.synthetic_exif(B, seed=78))
+    depth, conf, heat = _guided(model, x, ex, "top-left")
+    assert torch.isfinite(depth).all() and torch.allclose(heat.sum(-1), torch.ones(B, device=heat.device), atol=1e-5)
+    d2, _, h2 = _guided(model, x[40:42], {k: v[40:42] for k, v in ex.items()}, "top-left", replay_batch=B)
+    assert torch.equal(d2, depth[40:42]) and torch.equal(h2, heat[40:42])
