@@ -43,6 +43,16 @@ def _peaks():
     return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback of B200_PROFILING.md (file absent)"}
 
 
+def _profiled_traffic():
+    """DRAM bytes per dense-GEMM launch from the newest committed ncu capture (profiles/*_traffic.json), or None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    return d.get("dense_gemm_mean_bytes_per_launch"), os.path.basename(files[-1])
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -133,6 +143,8 @@ def run_candidate(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -261,7 +273,9 @@ def run_candidate(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": None,
+                     "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": _profiled_traffic()[0],
+                     "traffic_note": "mean DRAM read+write bytes per dense-GEMM launch, ncu capture %s (the captured "
+                                     "launches cover the QKV / proj / fc1 / fc2 shapes)" % _profiled_traffic()[1],
                      "kernel": "gemm_tcgen05_kernel (all dense epilogues)", "launches_per_step": g_n / args.steps,
                      "peak_source": peaks["source"],
                      "algorithmic_flops_per_launch_avg": g_w / max(g_n, 1)},

@@ -96,6 +96,34 @@ def kernels():
             f.write(f"| top warp-stall samples | {top} |\n\n")
 
 
+def traffic():
+    """Mean DRAM bytes (read + write) per launch of the dense GEMM kernel over the captured launches -> the
+    `roofline.traffic` figure bench.py reports next to the algorithmic work."""
+    import json
+    rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
+    if not os.path.exists(rep):
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, u = rows[0], rows[1]
+    idx = {n: i for i, n in enumerate(h)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    out = {}
+    for r in rows[2:]:
+        k = short(r[idx["Kernel Name"]])
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[idx[m]].replace(",", "")) * scale[u[idx[m]]]
+        out.setdefault(k, []).append(tot)
+    dense = [v for k, vs in out.items() if k.startswith("gemm_tcgen05_kernel<256") for v in vs]
+    res = {"tag": tag, "source": f"ncu --set full capture prof_{tag}.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum)",
+           "per_kernel_mean_bytes": {k: sum(v) / len(v) for k, v in out.items()},
+           "dense_gemm_mean_bytes_per_launch": sum(dense) / len(dense) if dense else None,
+           "dense_gemm_launches_captured": len(dense)}
+    json.dump(res, open(os.path.join(OUT, f"{tag}_traffic.json"), "w"), indent=1)
+
+
 launches()
 kernels()
+traffic()
 print("wrote", [p for p in os.listdir(OUT) if p.startswith(tag)])
