@@ -5,6 +5,7 @@
 #include "focal.cuh"
 #include "gemm.cuh"
 #include "heads.cuh"
+#include "visual.cuh"
 #include "rowops.cuh"
 #include "host.h"
 
@@ -110,9 +111,9 @@ int ca_focal_finalize(const float* pc, const float* cbias, float* attn, const fl
                                    static_cast<cudaStream_t>(stream));
 }
 
-int ca_guided_softmax(const float* base, const float* mask, float* heat, int32_t* argmax, int B, int N, float alpha,
-                      float temperature, void* stream) {
-  return ca::guided_softmax_launch(base, mask, heat, argmax, B, N, alpha, temperature,
+int ca_guided_softmax(const float* base, const float* mask, long long mask_batch_stride, float* heat, int32_t* argmax,
+                      int B, int N, float alpha, float temperature, void* stream) {
+  return ca::guided_softmax_launch(base, mask, mask_batch_stride, heat, argmax, B, N, alpha, temperature,
                                    static_cast<cudaStream_t>(stream));
 }
 
@@ -136,6 +137,10 @@ int ca_focal_value(const ca_focal_value_args* a, int B, void* stream) {
 int ca_focal_fusion(const float* feats, int n_iters, const float* w0, const float* b0, const float* w1, const float* b1,
                     float* out, int B, void* stream) {
   return ca::focal_fusion_launch(feats, n_iters, w0, b0, w1, b1, out, B, static_cast<cudaStream_t>(stream));
+}
+
+int ca_focus_map(const float* heat, int B, int g, int out_h, int out_w, float* norm, float* out, void* stream) {
+  return ca::focus_map_launch(heat, B, g, out_h, out_w, norm, out, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

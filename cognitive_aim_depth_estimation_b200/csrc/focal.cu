@@ -83,11 +83,13 @@ __global__ void __launch_bounds__(256) focal_finalize_kernel(const float* __rest
 
 // heat[b, :] = softmax((alpha*mask + (1-alpha)*base[b, :]) / temperature), argmax[b] = first index of the maximum
 __global__ void __launch_bounds__(256) guided_softmax_kernel(const float* __restrict__ base, const float* __restrict__ mask,
-                                                              float* __restrict__ heat, int* __restrict__ argmax, int N,
-                                                              float alpha, float temperature) {
+                                                              long long mask_batch_stride, float* __restrict__ heat,
+                                                              int* __restrict__ argmax, int N, float alpha,
+                                                              float temperature) {
   __shared__ float red[32];
   __shared__ int redi[32];
   const int b = blockIdx.x;
+  mask += static_cast<size_t>(b) * mask_batch_stride;  // 0: one instruction for the whole batch (src/model.py:1401)
   const float* bb = base + static_cast<size_t>(b) * N;
   float* hb = heat + static_cast<size_t>(b) * N;
   float mx = -INFINITY;
@@ -184,10 +186,11 @@ int focal_finalize_launch(const float* pc, const float* cbias, float* attn, cons
   return 0;
 }
 
-int guided_softmax_launch(const float* base, const float* mask, float* heat, int* argmax, int B, int N, float alpha,
-                          float temperature, cudaStream_t stream) {
+int guided_softmax_launch(const float* base, const float* mask, long long mask_batch_stride, float* heat, int* argmax,
+                          int B, int N, float alpha, float temperature, cudaStream_t stream) {
   CA_REQUIRE(base && mask && heat, "guided_softmax: null pointer");
-  guided_softmax_kernel<<<B, 256, 0, stream>>>(base, mask, heat, argmax, N, alpha, temperature);
+  CA_REQUIRE(mask_batch_stride == 0 || mask_batch_stride >= N, "guided_softmax: mask batch stride must be 0 or >= N");
+  guided_softmax_kernel<<<B, 256, 0, stream>>>(base, mask, mask_batch_stride, heat, argmax, N, alpha, temperature);
   CA_CUDA(cudaGetLastError());
   return 0;
 }

@@ -279,6 +279,10 @@ class CognitiveAimModel(nn.Module):
         return t
 
     def _mask(self, guidance, g: int) -> torch.Tensor:
+        """[N] mask of one instruction / guidance tensor, or [B, N] for a list of per-image instructions (a superset of
+        the reference, which broadcasts one instruction per call, src/model.py:1401)."""
+        if isinstance(guidance, (list, tuple)):
+            return torch.stack([self._mask(one, g) for one in guidance], dim=0)
         t = self._grid_tables(g)
         if isinstance(guidance, str):
             key = tables.canonical_instruction(guidance)
@@ -315,7 +319,7 @@ class CognitiveAimModel(nn.Module):
                 "focal_feat": torch.empty(B, 64, **fl), "fused": torch.empty(B, 192, **fl),
                 "depth": torch.empty(B, **fl), "conf": torch.empty(B, **fl),
                 # per-call inputs, at fixed addresses so that captured graphs can be replayed
-                "mask_in": torch.empty(N, **fl), "tmpw": torch.empty(64, _D, **fl), "tmpb": torch.empty(64, **fl),
+                "mask_in": torch.empty(B, N, **fl), "tmpw": torch.empty(64, _D, **fl), "tmpb": torch.empty(64, **fl),
                 "exif_in": torch.zeros(B, 3, **fl), "cam_in": torch.zeros(B, device=dev, dtype=torch.int64),
                 "graphs": {},
             }
@@ -505,6 +509,8 @@ class CognitiveAimModel(nn.Module):
         g = S // 14
         N, T = g * g, g * g + 1
         mask = self._mask(attention_guidance, g)
+        if mask.dim() == 2 and mask.shape[0] != B:
+            raise ValueError(f"{mask.shape[0]} per-image instructions for a batch of {B}")
         exif, cam = self._exif_tensors(exif_data, B)
         self._replay_reference_rng(B)
         tmp = nn.Linear(_D, 64)  # same constructor => same CPU-generator draws as src/model.py:1421
@@ -613,6 +619,26 @@ class CognitiveAimModel(nn.Module):
         ws["tokens"].copy_(tokens.to(self._device(), torch.float32))
         att = self._focal_iterations(ws, B, g, want_features).clone()
         return (att, ws["focal_feat"].clone()) if want_features else att
+
+    @torch.no_grad()
+    def focus_map(self, size, attention: Optional[torch.Tensor] = None):
+        """The overlay heat map `demo.py:_save_prediction_image` renders (demo.py:530-563): cube, 70th-percentile
+        threshold, min-max normalisation, g x g grid, order-1 zoom to `size` = (height, width) of the image it is laid
+        over — computed on the GPU from the attention of the last forward (or `attention` [B, N]) instead of numpy /
+        scipy on a D2H copy.  Returns float32 [B, height, width] in [0, 1]."""
+        att = self.get_attention_weights() if attention is None else attention
+        if att is None:
+            raise ValueError("no attention weights: run a forward pass first or pass `attention`")
+        att = att.to(self._device(), torch.float32).reshape(att.shape[0], -1).contiguous()
+        B, N = att.shape
+        g = int(math.isqrt(N))
+        if g * g != N:
+            raise ValueError("attention length must be a square grid")
+        h, w = int(size[0]), int(size[1])
+        norm = torch.empty(B, N, device=att.device, dtype=torch.float32)
+        out = torch.empty(B, h, w, device=att.device, dtype=torch.float32)
+        ops.focus_map(att, g, h, w, norm, out)
+        return out
 
     # -- demo-style preprocessing ---------------------------------------------------------------------------
     @torch.no_grad()

@@ -189,11 +189,15 @@ def focal_finalize(pc, cbias, attn, rs_in, rs_out, B, N, focus_strength=1.5, mod
 
 
 def guided_softmax(base, mask, heat, argmax, B, N, alpha=0.7, temperature=0.05):
+    """mask: [N] (one instruction for the batch) or [B, N] (one per image)."""
     _req(base, torch.float32, "base")
     _req(mask, torch.float32, "mask")
     _req(argmax, torch.int32, "argmax")
+    if mask.dim() == 2 and mask.shape[0] != B:
+        raise ValueError(f"per-image mask has {mask.shape[0]} rows for a batch of {B}")
+    stride = mask.stride(0) if mask.dim() == 2 else 0
     e0 = _begin()
-    check(_lib.load().ca_guided_softmax(ptr(base), ptr(mask), ptr(heat), ptr(argmax), B, N, alpha, temperature,
+    check(_lib.load().ca_guided_softmax(ptr(base), ptr(mask), stride, ptr(heat), ptr(argmax), B, N, alpha, temperature,
                                         stream_ptr()), "ca_guided_softmax")
     _end(e0, "small", 1)
 
@@ -203,6 +207,18 @@ def weighted_pool(src, src_batch_stride, row_offset, w, w2, partial, B, N, D, sp
     check(_lib.load().ca_weighted_pool(ptr(src), src_batch_stride, row_offset, ptr(w), ptr(w2), ptr(partial), B, N, D,
                                        splits, stream_ptr()), "ca_weighted_pool")
     _end(e0, "pool", 1, float(B * N * D * 4))
+
+
+def focus_map(heat, g, out_h, out_w, norm, out):
+    """norm [B, g*g], out [B, out_h, out_w] (or None): heat-map post-processing of demo.py:530-563 (csrc/visual.cu)."""
+    _req(heat, torch.float32, "heat")
+    _req(norm, torch.float32, "norm")
+    _req(out, torch.float32, "out")
+    B = heat.shape[0]
+    e0 = _begin()
+    check(_lib.load().ca_focus_map(ptr(heat), B, g, out_h, out_w, ptr(norm), ptr(out), stream_ptr()), "ca_focus_map")
+    _end(e0, "focus_map", 1 if out is None else 2, float(B * (2 * g * g + out_h * out_w) * 4))
+    return out if out is not None else norm
 
 
 def _dp(t):

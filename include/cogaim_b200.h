@@ -92,9 +92,11 @@ int ca_rowstats_merge(const float* pm, const float* ps, const float* weight, flo
 int ca_focal_finalize(const float* pc, const float* cbias, float* attn, const float* rs_in, float* rs_out, int B, int N,
                       int P, float focus_strength, int mode, void* stream);
 /* heat = softmax((alpha*mask + (1-alpha)*base)/temperature) per image; argmax = first index of the maximum.
- * src/model.py:1404-1409. */
-int ca_guided_softmax(const float* base, const float* mask, float* heat, int32_t* argmax, int B, int N, float alpha,
-                      float temperature, void* stream);
+ * src/model.py:1404-1409.  mask_batch_stride = 0: one mask [N] for the whole batch (the reference broadcasts one
+ * instruction per call, :1401); = N (or more): one mask per image, i.e. per-sample instructions in one batch
+ * (what demo.py:406-432 `predict_batch` does with a Python loop over single-image calls). */
+int ca_guided_softmax(const float* base, const float* mask, long long mask_batch_stride, float* heat, int32_t* argmax,
+                      int B, int N, float alpha, float temperature, void* stream);
 /* partial[b, s, :] = sum_{n in split s} w[b,n] * (w2 ? w2[b,n] : 1) * src[b*src_batch_stride + (row_offset+n)*D + :]
  * (src/model.py:1412-1414 guided pooling; :308 weighted features).  D must be 768. */
 int ca_weighted_pool(const float* src, long long src_batch_stride, int row_offset, const float* w, const float* w2,
@@ -146,6 +148,12 @@ int ca_focal_value(const ca_focal_value_args* a, int B, void* stream);
 /* fused[B,64] = IterativeFocalStream.fusion(cat(feats))  (src/model.py:430); feats is [B, n_iters, 64]. */
 int ca_focal_fusion(const float* feats, int n_iters, const float* w0, const float* b0, const float* w1, const float* b1,
                     float* out, int B, void* stream);
+
+/* ---- visualisation post-processing (the consumer right after the hot path; replaces demo.py:530-563) ------------
+ * norm[b, :]  = min-max( where(a > percentile70(a), a, 0.3 a) ),  a = heat[b, :]^3            (numpy float32 semantics)
+ * out[b,y,x]  = scipy.ndimage.zoom(norm[b].reshape(g, g), (out_h / g, out_w / g), order=1)    (skipped when out is null)
+ * heat, norm: [B, g*g] fp32; out: [B, out_h, out_w] fp32.  g*g <= 16384. */
+int ca_focus_map(const float* heat, int B, int g, int out_h, int out_w, float* norm, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -448,6 +448,24 @@ def forward_unguided(sd: SD, images: torch.Tensor, exif: Optional[dict], tokens=
 # --------------------------------------------------------------------------------------------------
 
 
+def focus_map(attention: torch.Tensor, height: int, width: int):
+    """demo.py:530-563, per image: cube, 70th-percentile threshold (x0.3 at or below), min-max, g x g, scipy zoom order 1
+    to the image size — with the very numpy / scipy calls the reference makes.  attention [B, N] -> float32 [B, h, w]."""
+    import numpy as np
+    from scipy.ndimage import zoom
+    outs = []
+    for row in attention.detach().cpu().numpy().astype(np.float32):
+        attn_map = np.power(row, 3)                                                   # :533
+        threshold = np.percentile(attn_map, 70)                                       # :536
+        attn_map = np.where(attn_map > threshold, attn_map, attn_map * 0.3)           # :537
+        attn_map = (attn_map - attn_map.min()) / (attn_map.max() - attn_map.min() + 1e-8)  # :540
+        g = int(np.sqrt(len(attn_map)))                                               # :543-546
+        assert g * g == len(attn_map)
+        m = attn_map.reshape(g, g)
+        outs.append(zoom(m, (height / g, width / g), order=1))                        # :558-563
+    return torch.from_numpy(np.stack(outs).astype(np.float32))
+
+
 def synthetic_images(B: int, S: int, seed: int = 1234) -> torch.Tensor:
     return torch.randn(B, 3, S, S, generator=torch.Generator().manual_seed(seed))
 

@@ -88,3 +88,26 @@ def test_cls_rows_and_focal_input(cuda_device):
     ops.cls_rows(x, cls, pos, B, N + 1, D)
     assert torch.equal(x[:, 0], (cls + pos[0]).expand(B, D))
     assert (x[:, 1:] == 0).all()
+
+
+@pytest.mark.parametrize("g,size", [(16, (224, 224)), (37, (518, 518)), (37, (480, 640)), (74, (300, 1036))])
+def test_focus_map_matches_numpy_scipy(cuda_device, g, size):
+    """Heat-map post-processing for visualisation (demo.py:530-563) on the GPU against the oracle, which runs the
+    reference's own numpy / scipy calls."""
+    from cognitive_aim_depth_estimation_b200 import ops
+    from oracle import cogaim_oracle as orc
+    B, N = 3, g * g
+    gen = torch.Generator().manual_seed(g)
+    heat = torch.softmax(torch.randn(B, N, generator=gen) * 3.0, dim=-1)
+    heat[1, :7] = heat[1, 7]  # ties around the order statistics
+    want = orc.focus_map(heat, *size)
+    norm = torch.empty(B, N, device=cuda_device)
+    out = torch.empty(B, *size, device=cuda_device)
+    ops.focus_map(heat.to(cuda_device), g, size[0], size[1], norm, out)
+    got = out.cpu()
+    assert got.shape == want.shape
+    assert float(got.min()) >= 0.0 and float(got.max()) <= 1.0
+    assert (got - want).abs().max().item() < 2e-6, (got - want).abs().max().item()
+    # the normalised grid itself (before the zoom) is exact up to numpy's powf vs x*x*x
+    ref_grid = orc.focus_map(heat, g, g)
+    assert (norm.cpu().view(B, g, g) - ref_grid).abs().max().item() < 2e-6

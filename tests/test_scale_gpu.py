@@ -123,3 +123,32 @@ def test_batch64_runs(model):
     assert torch.isfinite(depth).all() and torch.allclose(heat.sum(-1), torch.ones(B, device=heat.device), atol=1e-5)
     d2, _, h2 = _guided(model, x[40:42], {k: v[40:42] for k, v in ex.items()}, "top-left", replay_batch=B)
     assert torch.equal(d2, depth[40:42]) and torch.equal(h2, heat[40:42])
+
+
+def test_per_image_instructions_in_one_batch(model):
+    """one batch, one instruction PER IMAGE (demo.py:406-432 loops over single-image calls) ==
+    the rows of the nine single-instruction batched calls, bit for bit."""
+    B = 9
+    x = orc.synthetic_images(B, 224).cuda()
+    ex = _exif(orc.synthetic_exif(B))
+    instr = list(orc.INSTRUCTIONS)
+    depth, conf, heat = _guided(model, x, ex, instr)
+    for i, one in enumerate(instr):
+        d1, c1, h1 = _guided(model, x, ex, one)
+        assert torch.equal(d1[i], depth[i]) and torch.equal(c1[i], conf[i]) and torch.equal(h1[i], heat[i]), one
+    assert len({int(a) for a in heat.argmax(-1)}) > 1
+    with pytest.raises(ValueError):
+        model.forward_with_guidance(x, ex, instr[:4])
+
+
+def test_focus_map_of_last_forward(model):
+    """model.focus_map(): the overlay demo.py renders from get_attention_weights(), computed on the GPU."""
+    x = orc.synthetic_images(2, 224).cuda()
+    ex = _exif(orc.synthetic_exif(2))
+    _, _, heat = _guided(model, x, ex, "right")
+    fm = model.focus_map((200, 320))
+    want = orc.focus_map(heat.cpu(), 200, 320)
+    assert fm.shape == (2, 200, 320)
+    assert (fm.cpu() - want).abs().max().item() < 2e-6
+    with pytest.raises(ValueError):
+        model.focus_map((10, 10), attention=torch.zeros(1, 10).cuda())
