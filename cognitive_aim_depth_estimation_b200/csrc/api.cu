@@ -6,6 +6,7 @@
 #include "gemm.cuh"
 #include "heads.cuh"
 #include "visual.cuh"
+#include "resize.cuh"
 #include "rowops.cuh"
 #include "host.h"
 
@@ -137,6 +138,11 @@ int ca_focal_value(const ca_focal_value_args* a, int B, void* stream) {
 int ca_focal_fusion(const float* feats, int n_iters, const float* w0, const float* b0, const float* w1, const float* b1,
                     float* out, int B, void* stream) {
   return ca::focal_fusion_launch(feats, n_iters, w0, b0, w1, b1, out, B, static_cast<cudaStream_t>(stream));
+}
+
+int ca_resize_u8(const uint8_t* src, int B, int H0, int W0, int out_h, int out_w, uint8_t* tmp, uint8_t* out,
+                 void* stream) {
+  return ca::resize_u8_launch(src, B, H0, W0, out_h, out_w, tmp, out, static_cast<cudaStream_t>(stream));
 }
 
 int ca_focus_map(const float* heat, int B, int g, int out_h, int out_w, float* norm, float* out, void* stream) {

@@ -642,14 +642,35 @@ class CognitiveAimModel(nn.Module):
 
     # -- demo-style preprocessing ---------------------------------------------------------------------------
     @torch.no_grad()
-    def tokens_from_uint8(self, images_hwc_u8: torch.Tensor):
-        """uint8 [B, S, S, 3] (already at model resolution) -> backbone tokens, with ToTensor + Normalize + patchify
-        fused in one kernel (demo.py:162-166)."""
+    def preprocess(self, images_hwc_u8: torch.Tensor, size: int, mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD):
+        """demo.py:162-166 for a batch of same-sized uint8 [B, H, W, 3] images, on the GPU: Resize((size, size)) (Pillow's
+        antialiased bilinear resample, bit-exact) -> ToTensor -> Normalize.  Returns float32 [B, 3, size, size], the
+        tensor `forward` / `forward_with_guidance` take."""
         if images_hwc_u8.dtype != torch.uint8 or images_hwc_u8.dim() != 4 or images_hwc_u8.shape[-1] != 3:
-            raise ValueError("expected uint8 [B, S, S, 3]")
+            raise ValueError("expected uint8 [B, H, W, 3]")
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("preprocess runs only on a CUDA sm_100 device; there is no CPU fallback")
+        r = ops.resize_u8(images_hwc_u8.to(dev).contiguous(), size, size)
+        # ToTensor: a true division (a tensor divisor; dividing by a Python scalar multiplies by the reciprocal on CUDA)
+        x = r.permute(0, 3, 1, 2).to(torch.float32) / torch.full((1,), 255.0, device=dev)
+        m = torch.tensor(mean, device=dev).view(1, 3, 1, 1)
+        s = torch.tensor(std, device=dev).view(1, 3, 1, 1)
+        return x.sub_(m).div_(s).contiguous()                          # Normalize
+
+    @torch.no_grad()
+    def tokens_from_uint8(self, images_hwc_u8: torch.Tensor, size: Optional[int] = None):
+        """uint8 [B, H, W, 3] -> backbone tokens: demo.py:162-166 on the GPU — Resize((size, size)) exactly as Pillow does
+        it (skipped when the images already have that size or `size` is None), then ToTensor + Normalize + patchify
+        fused in one kernel."""
+        if images_hwc_u8.dtype != torch.uint8 or images_hwc_u8.dim() != 4 or images_hwc_u8.shape[-1] != 3:
+            raise ValueError("expected uint8 [B, H, W, 3]")
+        if size is not None and tuple(images_hwc_u8.shape[1:3]) != (size, size):
+            # demo.py:162-163 Resize((S, S)): Pillow's antialiased bilinear resample, bit-exact, on the GPU
+            images_hwc_u8 = ops.resize_u8(images_hwc_u8.to(self._device()).contiguous(), size, size)
         B, S = images_hwc_u8.shape[0], images_hwc_u8.shape[1]
         if images_hwc_u8.shape[2] != S:
-            raise ValueError("expected square images")
+            raise ValueError("expected square images (or pass size=S to resize like demo.py)")
         ws = self._workspace(B, S)
         patches = ops.preprocess_u8(images_hwc_u8.to(self._device()).contiguous(), ws["patches"])
         return self.backbone_tokens(None, patches=patches, B=B, S=S)

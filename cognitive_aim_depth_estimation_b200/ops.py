@@ -209,6 +209,20 @@ def weighted_pool(src, src_batch_stride, row_offset, w, w2, partial, B, N, D, sp
     _end(e0, "pool", 1, float(B * N * D * 4))
 
 
+def resize_u8(src, out_h, out_w):
+    """uint8 [B, H0, W0, 3] -> uint8 [B, out_h, out_w, 3], bit-exact PIL.Image.resize(..., BILINEAR) (csrc/resize.cu)."""
+    _req(src, torch.uint8, "src")
+    if src.dim() != 4 or src.shape[-1] != 3 or not src.is_contiguous():
+        raise ValueError("resize_u8 expects a contiguous uint8 [B, H, W, 3] tensor")
+    B, H0, W0, _ = src.shape
+    out = torch.empty(B, out_h, out_w, 3, device=src.device, dtype=torch.uint8)
+    tmp = torch.empty(B, H0, out_w, 3, device=src.device, dtype=torch.uint8) if (H0 != out_h and W0 != out_w) else None
+    e0 = _begin()
+    check(_lib.load().ca_resize_u8(ptr(src), B, H0, W0, out_h, out_w, ptr(tmp), ptr(out), stream_ptr()), "ca_resize_u8")
+    _end(e0, "resize", 2 if tmp is not None else 1, float(src.numel() + out.numel()))
+    return out
+
+
 def focus_map(heat, g, out_h, out_w, norm, out):
     """norm [B, g*g], out [B, out_h, out_w] (or None): heat-map post-processing of demo.py:530-563 (csrc/visual.cu)."""
     _req(heat, torch.float32, "heat")

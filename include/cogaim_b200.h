@@ -149,6 +149,13 @@ int ca_focal_value(const ca_focal_value_args* a, int B, void* stream);
 int ca_focal_fusion(const float* feats, int n_iters, const float* w0, const float* b0, const float* w1, const float* b1,
                     float* out, int B, void* stream);
 
+/* ---- demo.py:162-163 `Resize((S, S))` on a PIL image = Pillow's antialiased bilinear resample, bit-exact ----------
+ * src: uint8 [B, H0, W0, 3] (device), out: uint8 [B, out_h, out_w, 3].  tmp: uint8 [B, H0, out_w, 3] scratch, needed
+ * only when both axes change.  The fixed-point coefficient tables are built on the host as Pillow's Resample.c builds
+ * them and cached per (device, source size, target size) — the first call for a new size allocates and synchronises. */
+int ca_resize_u8(const uint8_t* src, int B, int H0, int W0, int out_h, int out_w, uint8_t* tmp, uint8_t* out,
+                 void* stream);
+
 /* ---- visualisation post-processing (the consumer right after the hot path; replaces demo.py:530-563) ------------
  * norm[b, :]  = min-max( where(a > percentile70(a), a, 0.3 a) ),  a = heat[b, :]^3            (numpy float32 semantics)
  * out[b,y,x]  = scipy.ndimage.zoom(norm[b].reshape(g, g), (out_h / g, out_w / g), order=1)    (skipped when out is null)

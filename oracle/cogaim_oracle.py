@@ -478,3 +478,97 @@ def synthetic_exif(B: int, seed: int = 1236) -> dict:
         "iso": torch.rand(B, generator=g) * 6350 + 50,
         "camera_idx": torch.randint(0, 71, (B,), generator=g),
     }
+
+
+# ------------------------------------------------------------------------------------------------------
+# demo.py:162-166 preprocessing: torchvision Resize((S,S)) on a PIL image = Pillow's antialiased bilinear resample.
+# Pillow is a third-party dependency of the reference (requirements.txt:8 `Pillow>=8.3.0`, unpinned; 12.2.0 here).
+# Restated from Pillow's published algorithm (src/libImaging/Resample.c: precompute_coeffs, normalize_coeffs_8bpc,
+# ImagingResampleHorizontal_8bpc / Vertical_8bpc, two passes with a uint8 intermediate); tests/test_oracle.py pins it
+# bit-exactly against PIL.Image.resize itself.
+# ------------------------------------------------------------------------------------------------------
+_PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def pil_bilinear_coeffs(in_size: int, out_size: int):
+    """Resample.c precompute_coeffs + normalize_coeffs_8bpc for the triangle filter (support 1.0), box = whole axis.
+    Returns (xmin[out], count[out], kk[out, ksize] int32)."""
+    import math
+    import numpy as np
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    xmin = np.zeros(out_size, np.int32)
+    cnt = np.zeros(out_size, np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        lo = int(center - support + 0.5)  # C (int) cast: truncation toward zero
+        lo = max(lo, 0)
+        hi = int(center + support + 0.5)
+        hi = min(hi, in_size)
+        n = hi - lo
+        w = np.zeros(ksize, np.float64)
+        for x in range(n):
+            t = abs((x + lo - center + 0.5) * ss)
+            w[x] = 1.0 - t if t < 1.0 else 0.0
+        ww = w[:n].sum() if n else 0.0
+        # Pillow accumulates ww sequentially in double; np.sum of <= ksize doubles may pair differently, so redo it
+        ww = 0.0
+        for x in range(n):
+            ww += w[x]
+        if ww != 0.0:
+            w[:n] /= ww
+        for x in range(n):
+            kk[xx, x] = int(-0.5 + w[x] * (1 << _PIL_PRECISION_BITS)) if w[x] < 0 else int(0.5 + w[x] * (1 << _PIL_PRECISION_BITS))
+        xmin[xx], cnt[xx] = lo, n
+    return xmin, cnt, kk
+
+
+def pil_resize_bilinear(img_u8, out_h: int, out_w: int):
+    """uint8 [H, W, C] -> uint8 [out_h, out_w, C] exactly as PIL.Image.resize((out_w, out_h), BILINEAR) (what
+    torchvision Resize((S, S)) calls for a PIL image, demo.py:162-163): horizontal pass, uint8 rounding, vertical pass."""
+    import numpy as np
+    img = np.asarray(img_u8)
+    H, W, _ = img.shape
+    if (H, W) == (out_h, out_w):
+        return img.copy()
+
+    def one_pass(src, out_size, axis):
+        xmin, cnt, kk = pil_bilinear_coeffs(src.shape[axis], out_size)
+        src = np.moveaxis(src, axis, 0).astype(np.int64)
+        acc = np.full((out_size,) + src.shape[1:], 1 << (_PIL_PRECISION_BITS - 1), np.int64)
+        for j in range(kk.shape[1]):
+            idx = np.minimum(xmin + j, src.shape[0] - 1)
+            coef = np.where(j < cnt, kk[:, j], 0).astype(np.int64)
+            acc += src[idx] * coef.reshape((-1,) + (1,) * (src.ndim - 1))
+        out = np.clip(acc >> _PIL_PRECISION_BITS, 0, 255).astype(np.uint8)
+        return np.moveaxis(out, 0, axis)
+
+    need_h, need_v = W != out_w, H != out_h
+    if need_h and need_v:
+        # Resample.c runs the horizontal pass only on the source rows the vertical pass will read
+        ymin, ycnt, _ = pil_bilinear_coeffs(H, out_h)
+        first, last = int(ymin[0]), int(ymin[-1] + ycnt[-1])
+        tmp = one_pass(img[first:last], out_w, 1)
+        xmin, cnt, kk = pil_bilinear_coeffs(H, out_h)
+        src = tmp.astype(np.int64)
+        acc = np.full((out_h,) + src.shape[1:], 1 << (_PIL_PRECISION_BITS - 1), np.int64)
+        for j in range(kk.shape[1]):
+            idx = np.minimum(xmin - first + j, src.shape[0] - 1)
+            coef = np.where(j < cnt, kk[:, j], 0).astype(np.int64)
+            acc += src[idx] * coef.reshape(-1, 1, 1)
+        return np.clip(acc >> _PIL_PRECISION_BITS, 0, 255).astype(np.uint8)
+    if need_h:
+        return one_pass(img, out_w, 1)
+    return one_pass(img, out_h, 0)
+
+
+def demo_preprocess(img_u8, S: int, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)) -> torch.Tensor:
+    """demo.py:162-166: Resize((S,S)) -> ToTensor -> Normalize, uint8 [H, W, 3] -> float32 [3, S, S]."""
+    import numpy as np
+    r = pil_resize_bilinear(img_u8, S, S)
+    x = torch.from_numpy(r.astype(np.float32) / np.float32(255.0)).permute(2, 0, 1)
+    return (x - torch.tensor(mean).view(3, 1, 1)) / torch.tensor(std).view(3, 1, 1)

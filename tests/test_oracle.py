@@ -97,3 +97,39 @@ def test_confidence_degenerate_constant():
     """SURVEY.md §4 degeneracy guard: at seed-0 init every confidence is sigmoid(2.0)."""
     gold = np.load(os.path.join(GOLD, "guided.npz"))
     assert np.allclose(gold["S224_B2_center_conf"], 0.8807970285, atol=1e-7)
+
+
+def test_pillow_resize_restatement_is_bit_exact():
+    """oracle.pil_resize_bilinear (restated from Pillow's Resample.c) against PIL.Image.resize itself — the third-party
+    arithmetic behind demo.py:162-163 `Resize((S, S))` (Pillow 12.2.0 here)."""
+    import numpy as np
+    from PIL import Image
+    from oracle import cogaim_oracle as orc
+    rng = np.random.default_rng(0)
+    for H, W, oh, ow in [(480, 640, 518, 518), (480, 640, 224, 224), (100, 77, 224, 224), (224, 224, 518, 518),
+                         (300, 518, 518, 518), (518, 300, 518, 518), (37, 41, 14, 70), (64, 64, 64, 64)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        want = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BILINEAR))
+        assert np.array_equal(orc.pil_resize_bilinear(img, oh, ow), want), (H, W, oh, ow)
+
+
+def test_demo_preprocess_restatement_matches_torchvision():
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    from oracle import cogaim_oracle as orc
+    img = np.random.default_rng(3).integers(0, 256, (120, 200, 3), dtype=np.uint8)
+    tf = transforms.Compose([transforms.Resize((56, 56)), transforms.ToTensor(),
+                             transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    assert torch.equal(orc.demo_preprocess(img, 56), tf(Image.fromarray(img)))
+
+
+def test_focus_map_restatement_shapes_and_range():
+    from oracle import cogaim_oracle as orc
+    heat = torch.softmax(torch.randn(2, 256, generator=torch.Generator().manual_seed(0)), -1)
+    fm = orc.focus_map(heat, 100, 150)
+    assert fm.shape == (2, 100, 150) and float(fm.min()) >= 0.0 and float(fm.max()) <= 1.0
+    grid = orc.focus_map(heat, 16, 16)  # identity zoom = the min-max normalised grid itself
+    assert abs(float(grid.max()) - 1.0) < 1e-4 and float(grid.min()) == 0.0  # (max - min) / (max - min + 1e-8)
+    # 70 % of the cubed cells sit at or below the percentile threshold and were scaled by 0.3
+    assert 0.6 < float((grid < grid.flatten(1).quantile(0.7, dim=1).view(2, 1, 1) + 1e-9).float().mean()) < 0.8

@@ -111,3 +111,38 @@ def test_focus_map_matches_numpy_scipy(cuda_device, g, size):
     # the normalised grid itself (before the zoom) is exact up to numpy's powf vs x*x*x
     ref_grid = orc.focus_map(heat, g, g)
     assert (norm.cpu().view(B, g, g) - ref_grid).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("H,W,oh,ow", [(480, 640, 518, 518), (480, 640, 224, 224), (1080, 1920, 518, 518),
+                                       (100, 77, 224, 224), (224, 224, 518, 518), (300, 518, 518, 518),
+                                       (518, 300, 518, 518), (37, 41, 14, 70), (518, 518, 518, 518)])
+def test_resize_matches_pillow(cuda_device, H, W, oh, ow):
+    """GPU resize == PIL.Image.resize(..., BILINEAR) bit for bit (demo.py:162-163 via torchvision Resize): down- and
+    up-scaling, one-axis-only, identity, ragged windows at the borders."""
+    import numpy as np
+    from PIL import Image
+    from cognitive_aim_depth_estimation_b200 import ops
+    rng = np.random.default_rng(H * 7 + W)
+    imgs = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+    imgs[1, : H // 2] = 255  # saturated region: exercises the 8-bit clamp
+    want = np.stack([np.asarray(Image.fromarray(i).resize((ow, oh), Image.BILINEAR)) for i in imgs])
+    got = ops.resize_u8(torch.from_numpy(imgs).to(cuda_device), oh, ow).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), int(np.abs(got.astype(int) - want.astype(int)).max())
+
+
+def test_preprocess_matches_torchvision(cuda_device):
+    """model.preprocess == torchvision Compose([Resize((S,S)), ToTensor(), Normalize(imagenet)]) (demo.py:162-166)."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    from cognitive_aim_depth_estimation_b200.model import create_model
+    cfg = {"model": {"cognitive_modules": ["ambient_stream", "iterative_focal_stream", "exif_prior_database"]}}
+    m = create_model(cfg, {"num_cameras": 71}, device=cuda_device)
+    rng = np.random.default_rng(5)
+    imgs = rng.integers(0, 256, (2, 480, 640, 3), dtype=np.uint8)
+    tf = transforms.Compose([transforms.Resize((224, 224)), transforms.ToTensor(),
+                             transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    want = torch.stack([tf(Image.fromarray(i)) for i in imgs])
+    got = m.preprocess(torch.from_numpy(imgs), 224).cpu()
+    assert torch.equal(got, want)
