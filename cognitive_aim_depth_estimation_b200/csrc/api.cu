@@ -101,9 +101,14 @@ int ca_focal_input(const float* tokens, const float* pe, const float* rowscale, 
                                 static_cast<cudaStream_t>(stream));
 }
 
-int ca_rowstats_merge(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, int rows, int P,
-                      void* stream) {
-  return ca::rowstats_merge_launch(pm, ps, weight, rmax, rinv, rows, P, static_cast<cudaStream_t>(stream));
+int ca_rowstats_merge(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, float* wtab,
+                      int rows, int P, void* stream) {
+  return ca::rowstats_merge_launch(pm, ps, weight, rmax, rinv, wtab, rows, P, static_cast<cudaStream_t>(stream));
+}
+
+int ca_colsum_e(const uint16_t* E, int lde, long long e_batch_stride, const float* wtab, float* pc, int B, int N, int P,
+                void* stream) {
+  return ca::colsum_e_launch(E, lde, e_batch_stride, wtab, pc, B, N, P, static_cast<cudaStream_t>(stream));
 }
 
 int ca_focal_finalize(const float* pc, const float* cbias, float* attn, const float* rs_in, float* rs_out, int B, int N,

@@ -55,10 +55,12 @@ constexpr uint32_t kTmemS = 0;      // two S buffers of 64 fp32 columns; P_i (bf
 constexpr uint32_t kTmemO = 128;    // 64 fp32 columns
 constexpr uint32_t kTmemQ = 192;    // 2 x 32 columns: Q tile of item k&1 as bf16x2 (A operand of every S MMA)
 constexpr int kItemQ = 8;            // depth of the per-CTA item queue (power of two)
-#ifndef CA_ATTN_POLY_PAIRS
-#define CA_ATTN_POLY_PAIRS 1
+// Split of the exp2 work between the MUFU and the FMA-pipe polynomial: 2 bits per group of 8 scores (4 pairs) = how many
+// of its pairs take the polynomial path; 8 groups per 64-key step.  0x5555 = one pair in every group = 25 %.
+#ifndef CA_ATTN_POLY_MASK
+#define CA_ATTN_POLY_MASK 0x5555
 #endif
-constexpr int kPolyPairs = CA_ATTN_POLY_PAIRS;  // of every 4 exp2 pairs, how many run on the FMA pipe (0..4)
+constexpr unsigned kPolyMask = CA_ATTN_POLY_MASK;
 constexpr float kLazyLimit = 8.0f;  // the accumulator reference moves only when a row max grew by > 2^8
 
 struct AttnArgs {
@@ -411,7 +413,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
 #pragma unroll
         for (int kk = 0; kk < 8; kk += 2) {
           ffma2(e[kk], e[kk + 1], __uint_as_float(v[8 * t + kk]), __uint_as_float(v[8 * t + kk + 1]), scale, neg_m);
-          if (kk >= 8 - 2 * kPolyPairs) {  // compile-time split between the MUFU and the polynomial path
+          if (kk >= 8 - 2 * static_cast<int>((kPolyMask >> (2 * t)) & 3u)) {  // compile-time split MUFU / polynomial
             exp2_poly2(e[kk], e[kk + 1]);
           } else {
             e[kk] = fast_exp2(e[kk]);

@@ -6,6 +6,8 @@
 // Reference: src/model.py:197-200,234-282 (FocalStream), :426 (re-focus), :1404-1414 (_guided_focal_stream).
 #include "common.cuh"
 #include "focal.cuh"
+
+#include <cuda_fp16.h>
 #include "host.h"
 
 namespace ca {
@@ -23,9 +25,11 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // pm, ps: [rows, P] (row max / sum-exp2 per 64-column span) -> rmax[rows], rinv[rows] = weight[row] / sum
+// wtab (optional): [rows, P], wtab[r, s] = exp2(m[r, s] - rmax[r]) * rinv[r] — the factor that turns the span-relative
+// exponentials E kept by GEMM pass A into (weighted) softmax probabilities.
 __global__ void rowstats_merge_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
                                       const float* __restrict__ weight, float* __restrict__ rmax,
-                                      float* __restrict__ rinv, int rows, int P) {
+                                      float* __restrict__ rinv, float* __restrict__ wtab, int rows, int P) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const float* m = pm + static_cast<size_t>(r) * P;
@@ -34,8 +38,46 @@ __global__ void rowstats_merge_kernel(const float* __restrict__ pm, const float*
   for (int i = 0; i < P; ++i) mx = fmaxf(mx, m[i]);
   float sum = 0.f;
   for (int i = 0; i < P; ++i) sum += s[i] * exp2f(m[i] - mx);  // s = 0 where the span is fully masked (m = -inf)
-  rmax[r] = mx;
-  rinv[r] = (weight ? weight[r] : 1.0f) / sum;
+  const float ri = (weight ? weight[r] : 1.0f) / sum;
+  if (rmax) rmax[r] = mx;
+  if (rinv) rinv[r] = ri;
+  if (wtab)
+    for (int i = 0; i < P; ++i) wtab[static_cast<size_t>(r) * P + i] = exp2f(m[i] - mx) * ri;
+}
+
+// Column sums of the (weighted) row softmax from the stored exponentials: pc[b, j, p] = sum over the 64 rows i of row
+// span p of E[b, i, j] * wtab[b, i, j / 64].  One thread = 8 consecutive columns (one 16-byte fp16 load per row);
+// grid = (column chunks, row spans, images).  Bandwidth-bound: reads E once (2 bytes per score).
+__global__ void __launch_bounds__(192) colsum_e_kernel(const __half* __restrict__ E, int lde, long long e_batch_stride,
+                                                        const float* __restrict__ wtab, float* __restrict__ pc, int N,
+                                                        int P) {
+  const int b = blockIdx.z;
+  const int p = blockIdx.y;
+  const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (j0 >= lde) return;
+  const int span = j0 >> 6;
+  const int i0 = p * 64;
+  const int i1 = min(i0 + 64, N);
+  const __half* e = E + static_cast<size_t>(b) * e_batch_stride + static_cast<size_t>(i0) * lde + j0;
+  const float* w = wtab + (static_cast<size_t>(b) * N + i0) * P + span;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+  for (int i = i0; i < i1; ++i) {
+    const uint4 q = *reinterpret_cast<const uint4*>(e);
+    const float wi = __ldg(w);
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __half22float2(h[t]);
+      acc[2 * t + 0] = fmaf(f.x, wi, acc[2 * t + 0]);
+      acc[2 * t + 1] = fmaf(f.y, wi, acc[2 * t + 1]);
+    }
+    e += lde;
+    w += P;
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+    if (j0 + t < N) pc[(static_cast<size_t>(b) * N + j0 + t) * P + p] = acc[t];
 }
 
 // One CTA per image.  pc: [B, N, P] column-sum partials.  attn[b, j] = final_attention of the iteration.
@@ -169,10 +211,23 @@ __global__ void __launch_bounds__(192) weighted_pool_kernel(const float* __restr
 
 }  // namespace
 
-int rowstats_merge_launch(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, int rows,
-                          int P, cudaStream_t stream) {
-  CA_REQUIRE(pm && ps && rmax && rinv, "rowstats_merge: null pointer");
-  rowstats_merge_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(pm, ps, weight, rmax, rinv, rows, P);
+int rowstats_merge_launch(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, float* wtab,
+                          int rows, int P, cudaStream_t stream) {
+  CA_REQUIRE(pm && ps, "rowstats_merge: null pointer");
+  CA_REQUIRE((rmax && rinv) || wtab, "rowstats_merge: no output requested");
+  rowstats_merge_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(pm, ps, weight, rmax, rinv, wtab, rows, P);
+  CA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int colsum_e_launch(const void* E, int lde, long long e_batch_stride, const float* wtab, float* pc, int B, int N, int P,
+                    cudaStream_t stream) {
+  CA_REQUIRE(E && wtab && pc, "colsum_e: null pointer");
+  CA_REQUIRE(lde % 64 == 0 && lde >= N, "colsum_e: lde must be a multiple of 64 and >= N");
+  CA_REQUIRE(P * 64 >= N && lde <= P * 64, "colsum_e: P row/column spans of 64 must cover N");
+  CA_REQUIRE((reinterpret_cast<uintptr_t>(E) & 15) == 0 && e_batch_stride % 8 == 0, "colsum_e: E must be 16-byte aligned");
+  dim3 grid((lde / 8 + 191) / 192, (N + 63) / 64, B);
+  colsum_e_kernel<<<grid, 192, 0, stream>>>(reinterpret_cast<const __half*>(E), lde, e_batch_stride, wtab, pc, N, P);
   CA_CUDA(cudaGetLastError());
   return 0;
 }

@@ -17,6 +17,8 @@
 // reference src/model.py:192-197).
 #include "common.cuh"
 #include "gemm.cuh"
+
+#include <cuda_fp16.h>
 #include "host.h"
 
 #include <stdlib.h>
@@ -114,15 +116,35 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
       }
     }
     float sum = 0.f;
+    // optional: keep the span-relative exponentials E = exp2(s - span max) as fp16 so that the column sums of the
+    // softmax are a bandwidth pass over E instead of a second Q K^T (ca_colsum_e)
+    __half* erow = p.out == nullptr ? nullptr
+                                    : reinterpret_cast<__half*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride +
+                                          static_cast<size_t>(row) * p.ldo + col_base;
 #pragma unroll
     for (int c = 0; c < kSpan; c += 32) {
       uint32_t v[32];
       tmem_ld32(taddr + c, v);
       tmem_ld_wait();
+      float ev[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float s = __uint_as_float(v[j]) * p.scale_log2;
-        if (col_base + c + j < p.N) sum += fast_exp2(s - mx);
+        ev[j] = (col_base + c + j < p.N) ? fast_exp2(s - mx) : 0.f;
+        sum += ev[j];
+      }
+      if (erow != nullptr && row_ok && col_base + c < p.ldo) {  // ldo is a multiple of 64: whole 32-column pieces
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 w;
+          __half2 h0 = __floats2half2_rn(ev[j + 0], ev[j + 1]), h1 = __floats2half2_rn(ev[j + 2], ev[j + 3]);
+          __half2 h2 = __floats2half2_rn(ev[j + 4], ev[j + 5]), h3 = __floats2half2_rn(ev[j + 6], ev[j + 7]);
+          w.x = *reinterpret_cast<uint32_t*>(&h0);
+          w.y = *reinterpret_cast<uint32_t*>(&h1);
+          w.z = *reinterpret_cast<uint32_t*>(&h2);
+          w.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(erow + c + j) = w;
+        }
       }
     }
     if (row_ok) {
@@ -493,10 +515,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           const uint32_t leader_full = mapa_cluster(smem_u32(&full_bar[stage]), 0);
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);  // both CTAs' bytes land here
-          tma_load_3d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, leader_full, kb * BK, mt2 * 2 * BM + rank * BM, b);
-          tma_load_3d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_w, leader_full, kb * BK, nt * BN + rank * (BN / 2),
-                          p.w_batched ? b : 0);
+          // CA_GEMM_DEBUG experiments (results are garbage): 1 = no B loads after the first K block, 2 = no A loads,
+          // 16 = every cluster loads tile (0, 0) (same L2 lines for everyone)
+          const bool la = !(p.dbg & 2) || kb == 0, lb = !(p.dbg & 1) || kb == 0;
+          const int mt_l = (p.dbg & 16) ? 0 : mt2, nt_l = (p.dbg & 16) ? 0 : nt;
+          if (rank == 0)  // both CTAs' bytes land on the leader's barrier
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * ((la ? Cfg::kABytes : 0) + (lb ? Cfg::kBBytes : 0)));
+          if (la) tma_load_3d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, leader_full, kb * BK, mt_l * 2 * BM + rank * BM, b);
+          if (lb)
+            tma_load_3d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_w, leader_full, kb * BK, nt_l * BN + rank * (BN / 2),
+                            p.w_batched ? b : 0);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1u;
@@ -626,6 +654,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     CA_REQUIRE(a.part_a != nullptr, "gemm: null partial buffer");
     CA_REQUIRE(a.epilogue != EPI_ROWSTATS || a.part_b != nullptr, "gemm: null partial-sum buffer");
     CA_REQUIRE(a.epilogue != EPI_COLSUM || (a.col_max && a.col_rinv), "gemm: null column statistics");
+    CA_REQUIRE(a.epilogue != EPI_ROWSTATS || a.out == nullptr || (a.ldo % 64 == 0 && a.ldo >= a.N),
+               "gemm: the exponential matrix needs a leading dimension that is a multiple of 64 and >= N");
   }
 
   // dense epilogues run on CTA pairs (cta_group::2) unless CA_GEMM_1CTA is set; the statistics epilogues keep the

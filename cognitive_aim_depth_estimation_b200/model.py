@@ -311,6 +311,10 @@ class CognitiveAimModel(nn.Module):
                 "xin": torch.empty(B * N, _D, **bf), "qk": torch.empty(B * N, 2 * _D, **bf),
                 "pm": torch.empty(B, N, P, **fl), "ps": torch.empty(B, N, P, **fl), "pc": torch.empty(B, N, P, **fl),
                 "rmax": torch.empty(B, N, **fl), "rinv": torch.empty(B, N, **fl),
+                # span-relative exponentials of the focal scores (fp16) + the per-(row, span) factors that turn them into
+                # softmax probabilities: the column sums are a bandwidth pass over E instead of a second Q K^T
+                "E": torch.empty(B, N, 64 * ((N + 63) // 64), device=dev, dtype=torch.float16),
+                "wtab": torch.empty(B, N, P, **fl),
                 "attn": torch.empty(self.cfg.num_iterations, B, N, **fl), "cvec": torch.empty(B, N, **fl),
                 "rowscale": torch.empty(2, B, N, **fl),
                 "heat": torch.empty(B, N, **fl), "argmax": torch.empty(B, device=dev, dtype=torch.int32),
@@ -431,16 +435,18 @@ class CognitiveAimModel(nn.Module):
             ops.gemm(ws["xin"], F_["wqk"], ops.EPI_BIAS_BF16, qk, bias=F_["bqk"])
             common = dict(M=N, N=N, K=_D, lda=2 * _D, ldw=2 * _D, batch=B, a_batch_stride=N * 2 * _D,
                           w_batch_stride=N * 2 * _D, scale_log2=scale_log2)
-            ops.gemm(q, k, ops.EPI_ROWSTATS, None, part_a=ws["pm"], part_b=ws["ps"], **common)
-            ops.rowstats_merge(ws["pm"], ws["ps"], None, ws["rmax"], ws["rinv"])
-            ops.gemm(k, q, ops.EPI_COLSUM, None, part_a=ws["pc"], col_max=ws["rmax"], col_rinv=ws["rinv"], **common)
+            E = ws["E"]
+            ops.gemm(q, k, ops.EPI_ROWSTATS, E, part_a=ws["pm"], part_b=ws["ps"], ldo=E.stride(1),
+                     out_batch_stride=E.stride(0), **common)
+            ops.rowstats_merge(ws["pm"], ws["ps"], None, None, None, ws["wtab"])
+            ops.colsum_e(E, ws["wtab"], ws["pc"], B, N)
             last = i == iters - 1
             rs_out = None if last else ws["rowscale"][i % 2]
             ops.focal_finalize(ws["pc"], tb["cbias"], ws["attn"][i], rs, rs_out, B, N, self.cfg.focus_strength, 0)
             if want_features:
                 # value path re-associated: sum_i a_i (A V)_i = ((a^T A) x~) Wv^T + bv   (src/model.py:204,308)
-                ops.rowstats_merge(ws["pm"], ws["ps"], ws["attn"][i], ws["rmax"], ws["rinv"])
-                ops.gemm(k, q, ops.EPI_COLSUM, None, part_a=ws["pc"], col_max=ws["rmax"], col_rinv=ws["rinv"], **common)
+                ops.rowstats_merge(ws["pm"], ws["ps"], ws["attn"][i], None, None, ws["wtab"])
+                ops.colsum_e(E, ws["wtab"], ws["pc"], B, N)
                 ops.focal_finalize(ws["pc"], None, ws["cvec"], None, None, B, N, 0.0, 1)
                 T = N + 1
                 ops.weighted_pool(ws["tokens"], T * _D, 1, ws["cvec"], rs, ws["pool"], B, N, _D, _POOL_SPLITS)

@@ -172,12 +172,24 @@ def focal_input(tokens, pe, rowscale, xin, B, N, D):
     return xin
 
 
-def rowstats_merge(pm, ps, weight, rmax, rinv):
+def rowstats_merge(pm, ps, weight, rmax, rinv, wtab=None):
     rows, P = pm.numel() // pm.shape[-1], pm.shape[-1]
     e0 = _begin()
-    check(_lib.load().ca_rowstats_merge(ptr(pm), ptr(ps), ptr(weight), ptr(rmax), ptr(rinv), rows, P, stream_ptr()),
-          "ca_rowstats_merge")
+    check(_lib.load().ca_rowstats_merge(ptr(pm), ptr(ps), ptr(weight), ptr(rmax), ptr(rinv), ptr(wtab), rows, P,
+                                        stream_ptr()), "ca_rowstats_merge")
     _end(e0, "small", 1)
+
+
+def colsum_e(E, wtab, pc, B, N):
+    """pc[B, N, P] column-sum partials of the (weighted) row softmax from the stored fp16 exponentials E [B, N, lde]."""
+    _req(E, torch.float16, "E")
+    _req(wtab, torch.float32, "wtab")
+    _req(pc, torch.float32, "pc")
+    P = pc.shape[-1]
+    e0 = _begin()
+    check(_lib.load().ca_colsum_e(ptr(E), E.stride(-2), E.stride(0), ptr(wtab), ptr(pc), B, N, P, stream_ptr()),
+          "ca_colsum_e")
+    _end(e0, "colsum_e", 1, float(E.numel() * 2))
 
 
 def focal_finalize(pc, cbias, attn, rs_in, rs_out, B, N, focus_strength=1.5, mode=0):

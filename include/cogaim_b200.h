@@ -38,7 +38,8 @@ typedef enum ca_epilogue {
   CA_EPI_GELU_BF16 = 1, /* out_bf16 = gelu_erf(acc + bias)            HF modeling_dinov2.py:324-326 (fc1 + GELU) */
   CA_EPI_RESID_F32 = 2, /* x_f32 += ls * (acc + bias), in place       HF modeling_dinov2.py:246,278,376-385 (dense + LayerScale + residual) */
   CA_EPI_PATCH_F32 = 3, /* x_f32[b*T+1+p] = acc + bias + pos[1+p]     HF modeling_dinov2.py:148,112 (patch conv + pos-embed) */
-  CA_EPI_ROWSTATS = 4,  /* softmax row statistics of acc*scale        src/model.py:197-200 (pass A, no N x N materialisation) */
+  CA_EPI_ROWSTATS = 4,  /* softmax row statistics of acc*scale        src/model.py:197-200 (pass A); with `out` != NULL also keeps
+                           exp2(acc*scale - span max) as fp16 [batch, M, ldo] for ca_colsum_e */
   CA_EPI_COLSUM = 5,    /* column sums of softmax(acc*scale)          src/model.py:234 (pass B, transposed) */
   CA_EPI_F32 = 6        /* out_f32 = acc (test hook) */
 } ca_epilogue;
@@ -82,10 +83,16 @@ int ca_focal_input(const float* tokens, const float* pe, const float* rowscale, 
                    void* stream);
 
 /* Focal / guidance vector stages (fp32) ---------------------------------------------------------- */
-/* Merge the per-64-column partials of CA_EPI_ROWSTATS: rmax[r] = max, rinv[r] = (weight ? weight[r] : 1) / sumexp.
+/* Merge the per-64-column partials of CA_EPI_ROWSTATS: rmax[r] = max, rinv[r] = (weight ? weight[r] : 1) / sumexp,
+ * wtab[r, s] = exp2(pm[r, s] - rmax[r]) * rinv[r]; any of the three outputs may be null (not all).
  * reference src/model.py:200 (row softmax statistics). */
-int ca_rowstats_merge(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, int rows, int P,
-                      void* stream);
+int ca_rowstats_merge(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, float* wtab,
+                      int rows, int P, void* stream);
+/* Column sums of the (weighted) row softmax from the span-relative exponentials E (fp16 [B, N, lde], written by
+ * ca_gemm_bf16 with CA_EPI_ROWSTATS when `out` is given): pc[b, j, p] = sum_{i in row span p} E[b,i,j] * wtab[b,i,j/64].
+ * Replaces the second Q K^T pass (CA_EPI_COLSUM) by one bandwidth-bound read of E.  src/model.py:234 (col mean), :308. */
+int ca_colsum_e(const uint16_t* E, int lde, long long e_batch_stride, const float* wtab, float* pc, int B, int N, int P,
+                void* stream);
 /* mode 0: FocalStream attention from CA_EPI_COLSUM partials: mean over rows + centre bias, L1 normalise, clamp 1e-8,
  *         renormalise; optionally rs_out = rs_in * (1 + focus_strength * attn)   (src/model.py:234-282, :426).
  * mode 1: attn = plain sum of the partials (weighted column sums of the un-guided value path). */

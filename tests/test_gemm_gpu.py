@@ -121,3 +121,32 @@ def test_gemm_focal_stats(cuda_device, N, D):
     colmean = pc.sum(-1) / N
     ref = torch.softmax(s, dim=-1).mean(dim=1)
     assert torch.allclose(colmean, ref, rtol=5e-3, atol=1e-7), (colmean - ref).abs().max()
+
+
+@pytest.mark.parametrize("N,D", [(256, 768), (1369, 768), (100, 768)])
+def test_focal_colsum_from_stored_exponentials(cuda_device, N, D):
+    """Pass A keeps exp2(s - span max) as fp16; ca_colsum_e turns it into the column sums of the row softmax
+    (== column mean of src/model.py:234 up to the 1/N), un-weighted and weighted (un-guided value path, :308)."""
+    from cognitive_aim_depth_estimation_b200 import ops
+    B = 2
+    q = _rand((B, N, D), cuda_device, 21).bfloat16()
+    k = _rand((B, N, D), cuda_device, 22, 0.5).bfloat16()
+    scale = 1.0 / math.sqrt(96.0)
+    P = ops.stats_partials(N)
+    pm = torch.zeros((B, N, P), device=cuda_device)
+    ps = torch.zeros((B, N, P), device=cuda_device)
+    lde = 64 * ((N + 63) // 64)
+    E = torch.full((B, N, lde), float("nan"), device=cuda_device, dtype=torch.float16)
+    ops.gemm(q, k, ops.EPI_ROWSTATS, E, M=N, N=N, K=D, lda=D, ldw=D, batch=B, a_batch_stride=N * D,
+             w_batch_stride=N * D, scale_log2=scale * ops.LOG2E, part_a=pm, part_b=ps, ldo=lde, out_batch_stride=N * lde)
+    assert torch.isfinite(E.float()).all() and float(E.max()) <= 1.0 and (E[:, :, N:] == 0).all()
+    s = torch.einsum("bid,bjd->bij", q.float(), k.float()) * scale
+    ref = torch.softmax(s, dim=-1)
+    for weight in (None, torch.rand(B, N, device=cuda_device)):
+        wtab = torch.empty((B, N, P), device=cuda_device)
+        pc = torch.zeros((B, N, P), device=cuda_device)
+        ops.rowstats_merge(pm, ps, weight, None, None, wtab)
+        ops.colsum_e(E, wtab, pc, B, N)
+        got = pc.sum(-1)
+        want = ref.sum(dim=1) if weight is None else (ref * weight[:, :, None]).sum(dim=1)
+        assert torch.allclose(got, want, rtol=3e-3, atol=1e-6), ((got - want).abs() / want).max()
