@@ -115,7 +115,7 @@ def traffic():
         for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(r[idx[m]].replace(",", "")) * scale[u[idx[m]]]
         out.setdefault(k, []).append(tot)
-    dense = [v for k, vs in out.items() if k.startswith("gemm_tcgen05_kernel<256") for v in vs]
+    dense = [v for k, vs in out.items() if k.startswith("gemm_tcgen05_kernel<256") or k.startswith("gemm2_tcgen05_kernel") for v in vs]
     res = {"tag": tag, "source": f"ncu --set full capture prof_{tag}.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum)",
            "per_kernel_mean_bytes": {k: sum(v) / len(v) for k, v in out.items()},
            "dense_gemm_mean_bytes_per_launch": sum(dense) / len(dense) if dense else None,
