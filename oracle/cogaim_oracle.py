@@ -11,7 +11,11 @@ What is restated (reference file:line given at each function):
   * reference src/model.py: AmbientStream, FocalStream, IterativeFocalStream, EXIFPriorDatabase,
     CuriosityModule (for its RNG draws and ring buffer), fusion + heads, `forward_with_guidance`,
     `_guided_focal_stream`, `forward`, and the construction order / custom inits of `create_model`
-    (so that `build_state_dict(seed)` reproduces the reference's random-init weights bit-for-bit).
+    (so that `build_state_dict(seed)` reproduces the reference's random-init weights bit-for-bit),
+  * reference demo.py:162-166 preprocessing: Pillow's antialiased bilinear resample (third-party, `Pillow>=8.3.0`
+    unpinned in requirements.txt:8; 12.2.0 here) restated from its Resample.c, ToTensor, Normalize
+    (`pil_resize_bilinear`, `demo_preprocess`) — pinned bit-exactly against PIL / torchvision in tests/test_oracle.py,
+  * reference demo.py:530-563 heat-map post-processing (`focus_map`), with the numpy / scipy calls the reference makes.
 
 Pinning: the reference ships no golden vectors or tests.  This oracle is pinned against
 outputs of the reference itself, imported unmodified in the build container by `oracle/make_golden.py`;
