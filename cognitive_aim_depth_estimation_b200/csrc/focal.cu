@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(192) colsum_e_kernel(const __half* __restrict_
   const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (j0 >= lde) return;
   const int span = j0 >> 6;
-  const int i0 = p * 64;
+  const int i0 = min(p * 64, N);
   const int i1 = min(i0 + 64, N);
   const __half* e = E + static_cast<size_t>(b) * e_batch_stride + static_cast<size_t>(i0) * lde + j0;
   const float* w = wtab + (static_cast<size_t>(b) * N + i0) * P + span;
@@ -226,7 +226,7 @@ int colsum_e_launch(const void* E, int lde, long long e_batch_stride, const floa
   CA_REQUIRE(lde % 64 == 0 && lde >= N, "colsum_e: lde must be a multiple of 64 and >= N");
   CA_REQUIRE(P * 64 >= N && lde <= P * 64, "colsum_e: P row/column spans of 64 must cover N");
   CA_REQUIRE((reinterpret_cast<uintptr_t>(E) & 15) == 0 && e_batch_stride % 8 == 0, "colsum_e: E must be 16-byte aligned");
-  dim3 grid((lde / 8 + 191) / 192, (N + 63) / 64, B);
+  dim3 grid((lde / 8 + 191) / 192, P, B);  // every partial slot is written (row spans past N contribute zeros)
   colsum_e_kernel<<<grid, 192, 0, stream>>>(reinterpret_cast<const __half*>(E), lde, e_batch_stride, wtab, pc, N, P);
   CA_CUDA(cudaGetLastError());
   return 0;

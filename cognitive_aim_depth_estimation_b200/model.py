@@ -327,6 +327,12 @@ class CognitiveAimModel(nn.Module):
                 "exif_in": torch.zeros(B, 3, **fl), "cam_in": torch.zeros(B, device=dev, dtype=torch.int64),
                 "graphs": {},
             }
+            if os.environ.get("CA_POISON_WS", "0") not in ("", "0"):
+                # test aid: every floating-point workspace starts as NaN, so a kernel that reads a slot nobody wrote
+                # (e.g. an unwritten partial-sum column) produces NaN instead of plausible stale data
+                for k, t in ws.items():
+                    if torch.is_tensor(t) and t.is_floating_point() and k not in ("exif_in",):
+                        t.fill_(float("nan"))
             if len(self._ws) >= 4:  # keep the cache bounded
                 self._ws.pop(next(iter(self._ws)))
             self._ws[key] = ws

@@ -8,6 +8,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+os.environ.setdefault("CA_POISON_WS", "1")  # NaN-filled workspaces: reads of never-written slots cannot hide
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a B200 (sm_100) GPU; run with -m gpu")
 

@@ -152,3 +152,44 @@ def test_focus_map_of_last_forward(model):
     assert (fm.cpu() - want).abs().max().item() < 2e-6
     with pytest.raises(ValueError):
         model.focus_map((10, 10), attention=torch.zeros(1, 10).cuda())
+
+
+def test_demo_single_image_path(model, sd):
+    """BASELINE.json configs[0]: demo.py's single-image call — a 480 x 640 uint8 image, Resize((224, 224)) as
+    experiment_B.yaml:87 / demo.py:154 configure it, instruction 'center', batch of ONE — GPU preprocessing + forward
+    against the oracle's preprocessing + forward."""
+    import numpy as np
+    img = np.random.default_rng(0).integers(0, 256, (480, 640, 3), dtype=np.uint8)  # stands in for the absent 1.jpg
+    x_ref = orc.demo_preprocess(img, 224).unsqueeze(0)
+    x_gpu = model.preprocess(torch.from_numpy(img).unsqueeze(0), 224)
+    assert torch.equal(x_gpu.cpu(), x_ref)
+    ex = {"focal_length": torch.tensor([50.0]), "aperture": torch.tensor([2.8]), "iso": torch.tensor([100.0]),
+          "camera_idx": torch.tensor([0])}  # demo.py:263-277 defaults
+    torch.manual_seed(11)
+    ref = orc.forward_with_guidance(sd, x_ref, ex, "center", update_history=False)
+    depth, conf, heat = _guided(model, x_gpu, _exif(ex), "center")
+    assert depth.shape == (1, 1) and heat.shape == (1, 256)
+    assert ((depth.cpu() - ref["depth"]).abs() / ref["depth"].abs()).max().item() <= 1e-2
+    assert (conf.cpu() - ref["confidence"]).abs().max().item() <= 1e-2
+    assert (heat.cpu() - ref["heatmap"]).abs().max().item() <= 1e-2
+    assert torch.equal(heat.cpu().argmax(-1), ref["heatmap"].argmax(-1))
+    # demo.py:355-356 reads the scalars back
+    assert abs(depth.squeeze().cpu().item() - ref["depth"].item()) / ref["depth"].item() <= 1e-2
+
+
+@pytest.mark.parametrize("S,B", [(56, 3), (70, 5), (126, 1)])
+def test_tiny_grids_and_odd_batches(model, sd, S, B):
+    """Smallest supported grids (4 x 4, 5 x 5, 9 x 9 patches: 17 / 26 / 82 tokens — every tile is ragged) and odd batch
+    sizes against the oracle."""
+    x = orc.synthetic_images(B, S, seed=S)
+    ex = orc.synthetic_exif(B, seed=S + 1)
+    torch.manual_seed(11)
+    ref = orc.forward_with_guidance(sd, x, ex, "top-right", update_history=False)
+    depth, conf, heat = _guided(model, x.cuda(), _exif(ex), "top-right")
+    assert ((depth.cpu() - ref["depth"]).abs() / ref["depth"].abs()).max().item() <= 1e-2
+    assert (heat.cpu() - ref["heatmap"]).abs().max().item() <= 1e-2
+    assert torch.equal(heat.cpu().argmax(-1), ref["heatmap"].argmax(-1))
+    ref_u = orc.forward_unguided(sd, x, ex, update_history=False)
+    d2, _, a2 = model(x.cuda(), _exif(ex), return_attention=True)
+    assert ((d2.cpu() - ref_u["depth"]).abs() / ref_u["depth"].abs()).max().item() <= 1e-2
+    assert (a2.cpu() - ref_u["heatmap"]).abs().max().item() <= 1e-2
