@@ -25,11 +25,12 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-S = 518
+S = 518  # overridden by --image-size (parity / sweep configs; the headline is 518)
 BATCH_PER_GPU = 32
 CFG = {"model": {"cognitive_modules": ["ambient_stream", "iterative_focal_stream", "exif_prior_database"]}}
 INSTRUCTIONS = ["center", "left", "right", "top", "bottom", "top-left", "top-right", "bottom-left", "bottom-right"]
-# algorithmic FLOPs per image at 518 (backbone 303.15 G + focal Q|K projection and one QK^T x3)
+# algorithmic FLOPs per image (backbone + focal Q|K projection and one QK^T x3)
+ALGO_GFLOP_BY_SIZE = {224: 48.4, 518: 321.5, 1036: 2218.0}
 ALGO_GFLOP_PER_IMAGE = 321.5
 METRIC = "images/sec at 518x518 bf16"
 
@@ -271,7 +272,7 @@ def run_candidate(args):
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "configs[1]: experiment_B full cognitive model, guided forward, 518x518, "
+        "config": {"workload": f"configs[1]: experiment_B full cognitive model, guided forward, {S}x{S}, "
                                f"batch {B}/GPU, 9 instructions cycled, random-init weights (seed 0)",
                    "batch_per_gpu": B, "global_batch": B * world, "image_size": S, "parallelism": f"batch-shard x{world}",
                    "l2": f"{n_sets} rotating resident input batches (3 x {B * 3 * S * S * 4 / 1e6:.0f} MB) + ~1 GB of "
@@ -316,7 +317,12 @@ def main():
     ap.add_argument("--impl", default="candidate", choices=["candidate", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--image-size", type=int, default=518, choices=sorted(ALGO_GFLOP_BY_SIZE),
+                    help="sweep configs of BASELINE.json (224 / 1036); the headline metric is quoted at 518")
     args = ap.parse_args()
+    global S, ALGO_GFLOP_PER_IMAGE, METRIC
+    S, ALGO_GFLOP_PER_IMAGE = args.image_size, ALGO_GFLOP_BY_SIZE[args.image_size]
+    METRIC = f"images/sec at {S}x{S} bf16"
     args.warmup = max(args.warmup, 3) if args.impl == "candidate" else args.warmup
     if args.impl == "reference":
         run_reference(args)
