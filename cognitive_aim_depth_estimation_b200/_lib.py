@@ -45,6 +45,20 @@ class FocalValueArgs(C.Structure):
                 ("proj_b1", C.c_void_p), ("feat_out", C.c_void_p), ("iter", C.c_int), ("n_iters", C.c_int)]
 
 
+class CuriosityWeights(C.Structure):
+    """ca_curiosity_weights (include/cogaim_b200.h)."""
+    _names = ["em_w0", "em_b0", "em_w1", "em_b1", "el_w0", "el_b0", "el_w1", "el_b1", "dec_w0", "dec_b0", "dec_w1",
+              "dec_b1", "unc_w0", "unc_b0", "unc_w1", "unc_b1", "loc_w0", "loc_b0", "loc_w1", "loc_b1", "cur_w"]
+    _fields_ = [(n, C.c_void_p) for n in _names]
+
+
+class CuriosityModWeights(C.Structure):
+    """ca_curiosity_mod_weights (include/cogaim_b200.h)."""
+    _fields_ = [("amp_w0", C.c_void_p), ("amp_b0", C.c_void_p), ("amp_w1", C.c_void_p), ("amp_b1", C.c_void_p),
+                ("mod_w0", C.c_void_p * 8), ("mod_b0", C.c_void_p * 8), ("mod_w1", C.c_void_p * 8),
+                ("mod_b1", C.c_void_p * 8)]
+
+
 # name -> (argtypes); every function returns int status except where noted
 _SIGNATURES = {
     "ca_version": [],
@@ -60,7 +74,12 @@ _SIGNATURES = {
     "ca_focal_input": [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr],
     "ca_rowstats_merge": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr],
     "ca_colsum_e": [c_ptr, C.c_int, C.c_longlong, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr],
-    "ca_focal_finalize": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, c_ptr],
+    "ca_focal_finalize": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, c_ptr,
+                          C.c_float, c_ptr],
+    "ca_curiosity": [C.POINTER(CuriosityWeights), c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr,
+                     C.c_int, c_ptr],
+    "ca_curiosity_modulation": [C.POINTER(CuriosityModWeights), c_ptr, C.c_float, C.c_float, c_ptr, C.c_int, C.c_int,
+                                C.c_int, c_ptr],
     "ca_resize_u8": [c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr],
     "ca_focus_map": [c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr],
     "ca_guided_softmax": [c_ptr, c_ptr, C.c_longlong, c_ptr, c_ptr, C.c_int, C.c_int, C.c_float, C.c_float, c_ptr],

@@ -2,6 +2,7 @@
 #include "../../include/cogaim_b200.h"
 
 #include "attention.cuh"
+#include "curiosity.cuh"
 #include "focal.cuh"
 #include "gemm.cuh"
 #include "heads.cuh"
@@ -112,9 +113,10 @@ int ca_colsum_e(const uint16_t* E, int lde, long long e_batch_stride, const floa
 }
 
 int ca_focal_finalize(const float* pc, const float* cbias, float* attn, const float* rs_in, float* rs_out, int B, int N,
-                      int P, float focus_strength, int mode, void* stream) {
-  return ca::focal_finalize_launch(pc, cbias, attn, rs_in, rs_out, B, N, P, focus_strength, mode,
-                                   static_cast<cudaStream_t>(stream));
+                      int P, float focus_strength, int mode, const float* cur_weight, float adaptive_weight,
+                      void* stream) {
+  return ca::focal_finalize_launch(pc, cbias, attn, rs_in, rs_out, B, N, P, focus_strength, mode, cur_weight,
+                                   adaptive_weight, static_cast<cudaStream_t>(stream));
 }
 
 int ca_guided_softmax(const float* base, const float* mask, long long mask_batch_stride, float* heat, int32_t* argmax,
@@ -143,6 +145,21 @@ int ca_focal_value(const ca_focal_value_args* a, int B, void* stream) {
 int ca_focal_fusion(const float* feats, int n_iters, const float* w0, const float* b0, const float* w1, const float* b1,
                     float* out, int B, void* stream) {
   return ca::focal_fusion_launch(feats, n_iters, w0, b0, w1, b1, out, B, static_cast<cudaStream_t>(stream));
+}
+
+int ca_curiosity(const ca_curiosity_weights* w, const float* tokens, int tokens_per_img, const float* eps,
+                 const float* noise, float* reward_raw, float* reward, float* history, int history_len,
+                 long long* history_pointer, int B, void* stream) {
+  if (!w) return ca::invalid("curiosity: null weight struct");
+  return ca::curiosity_launch(*w, tokens, tokens_per_img, eps, noise, reward_raw, reward, history, history_len,
+                              history_pointer, B, static_cast<cudaStream_t>(stream));
+}
+
+int ca_curiosity_modulation(const ca_curiosity_mod_weights* w, const float* reward, float lo, float hi, float* cur_weight,
+                            int B, int n_iters, int mod_hidden, void* stream) {
+  if (!w) return ca::invalid("curiosity_modulation: null weight struct");
+  return ca::curiosity_modulation_launch(*w, reward, lo, hi, cur_weight, B, n_iters, mod_hidden,
+                                         static_cast<cudaStream_t>(stream));
 }
 
 int ca_resize_u8(const uint8_t* src, int B, int H0, int W0, int out_h, int out_w, uint8_t* tmp, uint8_t* out,

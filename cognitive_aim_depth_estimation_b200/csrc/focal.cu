@@ -84,10 +84,13 @@ __global__ void __launch_bounds__(192) colsum_e_kernel(const __half* __restrict_
 // rowscale_out[b, j] = rowscale_in[b, j] * (1 + focus_strength * attn)  when rowscale_out != nullptr.
 // mode 0: FocalStream attention  (mean over rows, centre bias, L1, clamp, renorm)   src/model.py:234-282
 // mode 1: plain sum of partials (weighted column sums for the un-guided value path; no bias / normalisation)
+// cur_weight[b] (optional): curiosity modulation between the L1 normalisation and the clamp (src/model.py:264-276).
 __global__ void __launch_bounds__(256) focal_finalize_kernel(const float* __restrict__ pc, const float* __restrict__ cbias,
                                                               float* __restrict__ attn, const float* __restrict__ rs_in,
                                                               float* __restrict__ rs_out, int N, int P,
-                                                              float focus_strength, int mode) {
+                                                              float focus_strength, int mode,
+                                                              const float* __restrict__ cur_weight,
+                                                              float adaptive_weight) {
   __shared__ float red[32];
   const int b = blockIdx.x;
   const float* pcb = pc + static_cast<size_t>(b) * N * P;
@@ -105,9 +108,12 @@ __global__ void __launch_bounds__(256) focal_finalize_kernel(const float* __rest
   if (mode != 0) return;
   const float tot1 = block_sum(local, red);
   const float d1 = tot1 + 1e-8f;
+  const float cw = cur_weight ? cur_weight[b] : 0.f;
   local = 0.f;
   for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    const float v = fmaxf(ab[j] / d1, 1e-8f);
+    float v = ab[j] / d1;
+    if (cur_weight) v = adaptive_weight * (v * (1.0f + cw)) + (1.0f - adaptive_weight) * v;  // src/model.py:270-274
+    v = fmaxf(v, 1e-8f);
     ab[j] = v;
     local += v;
   }
@@ -233,10 +239,12 @@ int colsum_e_launch(const void* E, int lde, long long e_batch_stride, const floa
 }
 
 int focal_finalize_launch(const float* pc, const float* cbias, float* attn, const float* rs_in, float* rs_out, int B,
-                          int N, int P, float focus_strength, int mode, cudaStream_t stream) {
+                          int N, int P, float focus_strength, int mode, const float* cur_weight, float adaptive_weight,
+                          cudaStream_t stream) {
   CA_REQUIRE(pc && attn, "focal_finalize: null pointer");
   CA_REQUIRE(mode != 0 || cbias, "focal_finalize: null centre bias");
-  focal_finalize_kernel<<<B, 256, 0, stream>>>(pc, cbias, attn, rs_in, rs_out, N, P, focus_strength, mode);
+  focal_finalize_kernel<<<B, 256, 0, stream>>>(pc, cbias, attn, rs_in, rs_out, N, P, focus_strength, mode,
+                                                  cur_weight, adaptive_weight);
   CA_CUDA(cudaGetLastError());
   return 0;
 }

@@ -10,7 +10,8 @@ int rowstats_merge_launch(const float* pm, const float* ps, const float* weight,
 int colsum_e_launch(const void* E, int lde, long long e_batch_stride, const float* wtab, float* pc, int B, int N, int P,
                     cudaStream_t stream);
 int focal_finalize_launch(const float* pc, const float* cbias, float* attn, const float* rs_in, float* rs_out, int B,
-                          int N, int P, float focus_strength, int mode, cudaStream_t stream);
+                          int N, int P, float focus_strength, int mode, const float* cur_weight, float adaptive_weight,
+                          cudaStream_t stream);
 int guided_softmax_launch(const float* base, const float* mask, long long mask_batch_stride, float* heat, int* argmax,
                           int B, int N, float alpha, float temperature, cudaStream_t stream);
 int weighted_pool_launch(const float* src, long long src_batch_stride, int row_offset, const float* w, const float* w2,

@@ -9,10 +9,13 @@ Differences that are deliberate:
   * the forward runs ONLY on a CUDA sm_100 device through libcogaim_b200.so; there is no CPU fallback and errors
     are raised, never swallowed (the reference prints and falls back, src/model.py:1050-1056,1237-1240);
   * the reference's redundant passes (backbone x3, focal stream x4 in `forward`) are computed once;
-  * output-dead work of the effective configuration (value path / projections in guided mode, CuriosityModule
-    score, DimensionAligners, LoRA) is not executed; the CuriosityModule's two `randn_like` draws are replayed on
-    the CPU generator so that the per-call random projection (src/model.py:1421) matches the reference under a
-    shared `torch.manual_seed`.
+  * output-dead work of the effective configuration (value path / projections in guided mode, DimensionAligners,
+    LoRA) is not executed;
+  * the CuriosityModule (src/model.py:586-688) runs on the GPU as often as the reference runs it (once per guided call,
+    one to three times per `forward`), for its observable state — the `exploration_history` ring buffer and
+    `history_pointer` — and, with `curiosity_guided_attention.enabled`, for the attention modulation.  Its two
+    `randn_like` draws per run come from the global CPU generator, where a CPU reference takes them, so that the
+    per-call random projection (src/model.py:1421) matches the reference under a shared `torch.manual_seed`.
 """
 from __future__ import annotations
 
@@ -31,6 +34,7 @@ _HEADS = 12
 _LAYERS = 12
 _MLP = 3072
 _POOL_SPLITS = 8
+_MAX_CURIOSITY_RUNS = 3
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -69,7 +73,12 @@ def _param_specs(cfg: EffectiveConfig):
         p = f"focal_stream.focal_streams.{i}."
         s += [(p + "adaptive_weight", (), "const:0.5")]
         s += lin(p + "query_proj", _D, _D) + lin(p + "key_proj", _D, _D) + lin(p + "value_proj", _D, _D)
+        if cfg.curiosity_guided:  # src/model.py:73-79
+            s += lin(p + "curiosity_modulator.0", h // 8, 1) + lin(p + "curiosity_modulator.2", 8, h // 8)
         s += lin(p + "projection.0", h, _D) + lin(p + "projection.3", h // 4, h)
+    if cfg.curiosity_guided:  # src/model.py:333-339
+        s += lin("focal_stream.curiosity_amplifier.0", 32, 1)
+        s += lin("focal_stream.curiosity_amplifier.2", cfg.num_iterations, 32)
     s += lin("focal_stream.fusion.0", h // 2, h // 4 * cfg.num_iterations) + lin("focal_stream.fusion.2", h // 4, h // 2)
     if cfg.use_exif:
         s += [("exif_prior.camera_embedding.weight", (cfg.num_cameras, 64), "w")]
@@ -122,8 +131,8 @@ class CognitiveAimModel(nn.Module):
             raise NotImplementedError(
                 "the B200 path is built for the configuration every shipped YAML resolves to "
                 "(ambient_stream + iterative_focal_stream [+ exif_prior_database]); got cognitive_modules without them")
-        if cfg.curiosity_guided:
-            raise NotImplementedError("curiosity_guided_attention.enabled=True is not built (SURVEY.md §8f rank 4)")
+        if cfg.num_iterations > 8:
+            raise NotImplementedError("at most 8 focal iterations are built")
         # attributes demo.py reads (demo.py:71-73,380-382)
         self.backbone_size = cfg.backbone_size
         self.feature_dim = cfg.feature_dim
@@ -157,6 +166,7 @@ class CognitiveAimModel(nn.Module):
         self._ws: Dict = {}       # workspaces keyed by (B, S)
         self.validate_inputs = True
         self.rng_replay_batch = None  # sharded runs: replay the reference's RNG draws at the GLOBAL batch size
+        self.rng_replay_offset = 0    # ... and take this shard's rows of them
         # The ~110 launches of one forward are captured once per (batch, resolution, path) into a CUDA graph and
         # replayed: the launch gaps between dependent kernels (~0.4 ms of a 14 ms step) and the host-side launch work
         # disappear.  Per-call inputs (mask, per-call projection, EXIF) are copied into fixed buffers the graph reads.
@@ -259,6 +269,32 @@ class CognitiveAimModel(nn.Module):
         }
         pk["heads_tensors"] = hw
         pk["heads"] = ops.make_heads_weights(hw)
+        c = "curiosity_module."
+        cw = {}
+        for short, name in (("em", "encoder_mean"), ("el", "encoder_logvar"), ("dec", "decoder")):
+            cw[short + "_w0"], cw[short + "_b0"] = f32(sd[c + name + ".0.weight"]), f32(sd[c + name + ".0.bias"])
+            cw[short + "_w1"], cw[short + "_b1"] = f32(sd[c + name + ".3.weight"]), f32(sd[c + name + ".3.bias"])
+        cw["unc_w0"], cw["unc_b0"] = f32(sd[c + "uncertainty_head.0.weight"]), f32(sd[c + "uncertainty_head.0.bias"])
+        cw["unc_w1"], cw["unc_b1"] = f32(sd[c + "uncertainty_head.2.weight"]), f32(sd[c + "uncertainty_head.2.bias"])
+        if self.cfg.enable_hierarchical_curiosity:
+            cw["loc_w0"], cw["loc_b0"] = f32(sd[c + "local_curiosity.0.weight"]), f32(sd[c + "local_curiosity.0.bias"])
+            cw["loc_w1"], cw["loc_b1"] = f32(sd[c + "local_curiosity.2.weight"]), f32(sd[c + "local_curiosity.2.bias"])
+        cw["cur_w"] = f32(sd[c + "curiosity_weights"])
+        pk["curiosity_tensors"] = cw
+        pk["curiosity"] = ops.make_curiosity_weights(cw)
+        pk["curiosity_mod"] = None
+        if self.cfg.curiosity_guided:
+            fsp = "focal_stream."
+            amp = tuple(f32(sd[fsp + n]) for n in ("curiosity_amplifier.0.weight", "curiosity_amplifier.0.bias",
+                                                   "curiosity_amplifier.2.weight", "curiosity_amplifier.2.bias"))
+            mods = []
+            for i in range(self.cfg.num_iterations):
+                q = f"{fsp}focal_streams.{i}.curiosity_modulator."
+                mods.append(tuple(f32(sd[q + n]) for n in ("0.weight", "0.bias", "2.weight", "2.bias")))
+            pk["curiosity_mod_tensors"] = (amp, mods)
+            pk["curiosity_mod"] = ops.make_curiosity_mod_weights(amp, mods)
+            pk["adaptive_weight"] = [float(sd[f"{fsp}focal_streams.{i}.adaptive_weight"])
+                                     for i in range(self.cfg.num_iterations)]
         pk["pos_param"] = sd[e + "position_embeddings"]
         self._packed = pk
         return pk
@@ -325,6 +361,14 @@ class CognitiveAimModel(nn.Module):
                 # per-call inputs, at fixed addresses so that captured graphs can be replayed
                 "mask_in": torch.empty(B, N, **fl), "tmpw": torch.empty(64, _D, **fl), "tmpb": torch.empty(64, **fl),
                 "exif_in": torch.zeros(B, 3, **fl), "cam_in": torch.zeros(B, device=dev, dtype=torch.int64),
+                # CuriosityModule: up to _MAX_CURIOSITY_RUNS runs per call (src/model.py:992,1104,1138,1185), each with
+                # its own pair of Gaussian draws; rewards per run; modulation weights per (run, iteration)
+                "cur_eps": torch.zeros(_MAX_CURIOSITY_RUNS, B, 192, **fl),
+                "cur_noise": torch.zeros(_MAX_CURIOSITY_RUNS, B, _D, **fl),
+                "cur_raw": torch.empty(_MAX_CURIOSITY_RUNS, B, **fl),
+                "cur_reward": torch.empty(_MAX_CURIOSITY_RUNS, B, **fl),
+                "cur_weight": torch.empty(_MAX_CURIOSITY_RUNS, self.cfg.num_iterations, B, **fl),
+                "att_run": torch.empty(_MAX_CURIOSITY_RUNS, B, N, **fl),
                 "graphs": {},
             }
             if os.environ.get("CA_POISON_WS", "0") not in ("", "0"):
@@ -340,17 +384,31 @@ class CognitiveAimModel(nn.Module):
 
     # -- stages -----------------------------------------------------------------------------------------
     def _pinned_slot(self):
-        """Next buffer of a 4-deep ring of pinned host staging areas for the per-call projection; waits (normally not
-        at all: the copy is four calls old) until the previous async copy out of it has completed."""
+        """Next buffer of a 4-deep ring of pinned host staging areas for the per-call projection and the curiosity
+        draws; waits (normally not at all: the copy is four calls old) until the previous async copy out of it has
+        completed."""
         ring = getattr(self, "_pinned_ring", None)
         if ring is None:
             ring = {"slots": [{"w": torch.empty(64, _D).pin_memory(), "b": torch.empty(64).pin_memory(),
-                               "event": torch.cuda.Event()} for _ in range(4)], "next": 0}
+                               "eps": None, "noise": None, "event": torch.cuda.Event()} for _ in range(4)], "next": 0}
             self._pinned_ring = ring
         slot = ring["slots"][ring["next"]]
         ring["next"] = (ring["next"] + 1) % len(ring["slots"])
         slot["event"].synchronize()
         return slot
+
+    def _stage_draws(self, ws, slot, draws):
+        """Curiosity draws [(eps [B,192], noise [B,768]), ...] -> pinned staging -> the fixed device buffers the
+        (possibly graph-captured) curiosity kernel reads."""
+        k, B = len(draws), draws[0][0].shape[0]
+        if slot["eps"] is None or slot["eps"].shape[1] < B:
+            slot["eps"] = torch.empty(_MAX_CURIOSITY_RUNS, B, 192).pin_memory()
+            slot["noise"] = torch.empty(_MAX_CURIOSITY_RUNS, B, _D).pin_memory()
+        for j, (eps, noise) in enumerate(draws):
+            slot["eps"][j, :B].copy_(eps)
+            slot["noise"][j, :B].copy_(noise)
+        ws["cur_eps"][:k].copy_(slot["eps"][:k, :B], non_blocking=True)
+        ws["cur_noise"][:k].copy_(slot["noise"][:k, :B], non_blocking=True)
 
     @staticmethod
     def _check_images(images):
@@ -423,9 +481,10 @@ class CognitiveAimModel(nn.Module):
         graph[0].replay()
         ops.count_launches(graph[1])
 
-    def _focal_iterations(self, ws, B: int, g: int, want_features: bool):
-        """IterativeFocalStream (src/model.py:391-455): per iteration Q|K projection, two tensor-core passes over
-        Q K^T (row statistics, then column sums in the transposed orientation) and the vector epilogue.
+    def _focal_iterations(self, ws, B: int, g: int, want_features: bool, cur_weight=None):
+        """IterativeFocalStream (src/model.py:391-455): per iteration Q|K projection, one tensor-core pass over Q K^T
+        (row statistics + stored exponentials), the column sums as a bandwidth pass, and the vector epilogue.
+        `cur_weight` [n_iters, B]: curiosity modulation (only with curiosity_guided_attention.enabled, :264-276).
         Returns the last iteration's attention [B, N]; fills ws['focal_feat'] when `want_features`."""
         pk = self._pack()
         tb = self._grid_tables(g)
@@ -448,7 +507,9 @@ class CognitiveAimModel(nn.Module):
             ops.colsum_e(E, ws["wtab"], ws["pc"], B, N)
             last = i == iters - 1
             rs_out = None if last else ws["rowscale"][i % 2]
-            ops.focal_finalize(ws["pc"], tb["cbias"], ws["attn"][i], rs, rs_out, B, N, self.cfg.focus_strength, 0)
+            ops.focal_finalize(ws["pc"], tb["cbias"], ws["attn"][i], rs, rs_out, B, N, self.cfg.focus_strength, 0,
+                               cur_weight=None if cur_weight is None else cur_weight[i],
+                               adaptive_weight=pk["adaptive_weight"][i] if cur_weight is not None else 0.5)
             if want_features:
                 # value path re-associated: sum_i a_i (A V)_i = ((a^T A) x~) Wv^T + bv   (src/model.py:204,308)
                 ops.rowstats_merge(ws["pm"], ws["ps"], ws["attn"][i], None, None, ws["wtab"])
@@ -488,13 +549,35 @@ class CognitiveAimModel(nn.Module):
             raise ValueError("camera_idx out of range")  # (one tiny D2H sync; disable for CUDA-graph capture)
         return cont, cam
 
-    def _replay_reference_rng(self, B: int):
-        """CuriosityModule draws randn(B,192) then randn(B,768) on the global CPU generator in eval
-        (src/model.py:609,744) before the per-call projection is initialised (:1421).  A batch-sharded run sets
-        `rng_replay_batch` to the global batch so every shard sees the projection of the un-sharded call."""
-        B = self.rng_replay_batch or B
-        torch.randn(B, 192)
-        torch.randn(B, 768)
+    def _curiosity_draw(self, B: int):
+        """One CuriosityModule run draws randn(B,192) then randn(B,768) on the global CPU generator in eval
+        (src/model.py:609,744), before the per-call projection is initialised (:1421).  A batch-sharded run sets
+        `rng_replay_batch` / `rng_replay_offset` to the global batch / this shard's first image so every shard sees the
+        draws (and hence the projection) of the un-sharded call.  Returns this shard's (eps [B,192], noise [B,768])."""
+        Bg = self.rng_replay_batch or B
+        lo = self.rng_replay_offset if self.rng_replay_batch else 0
+        eps = torch.randn(Bg, 192)
+        noise = torch.randn(Bg, 768)
+        return eps[lo:lo + B], noise[lo:lo + B]
+
+    def _curiosity_runs(self, ws, B: int, T: int, roles):
+        """Device side of the CuriosityModule runs of one call, in the reference's order: rewards, ring-buffer update,
+        and (curiosity-guided configuration only) the attention modulation weights of each run.  The score of the
+        un-guided attention runs is clamped to [0.5, 1] (src/model.py:1107, :1141); the others are not."""
+        pk = self._packed
+        cm = self.curiosity_module
+        for j, role in enumerate(roles):
+            ops.curiosity(pk["curiosity"], tokens=ws["tokens"], tokens_per_img=T, eps=ws["cur_eps"][j],
+                          noise=ws["cur_noise"][j], reward_raw=ws["cur_raw"][j], reward=ws["cur_reward"][j],
+                          history=cm.exploration_history, history_pointer=cm.history_pointer, B=B)
+            if self.cfg.curiosity_guided:
+                lo, hi = (0.5, 1.0) if role in ("last", "ret") else (1.0, 0.0)
+                ops.curiosity_modulation(pk["curiosity_mod"], ws["cur_reward"][j], lo, hi, ws["cur_weight"][j], B,
+                                         self.cfg.num_iterations, self.cfg.focal_hidden_dim // 8)
+
+    def _curiosity_key(self):
+        cm = self.curiosity_module
+        return (cm.exploration_history.data_ptr(), cm.history_pointer.data_ptr())
 
     # -- public forward passes --------------------------------------------------------------------------
     @torch.no_grad()
@@ -502,19 +585,12 @@ class CognitiveAimModel(nn.Module):
         """reference src/model.py:1157-1240.  Returns (depth [B,1], confidence [B,1][, attention [B,N]])."""
         if attention_guidance is None and exif_data is not None and self.use_exif:
             # guidance None -> plain focal-stream features and attention (:1206-1212)
-            return self._forward_impl(images, exif_data, return_attention, keep_last=False)
+            return self._forward_impl(images, exif_data, return_attention, mode="guided_none")
         if exif_data is None or not self.use_exif:
             # reference: the 128-wide concat fails inside `fusion`, the except branch falls back to forward()
             # (:1237-1240) AFTER the guided attention was stored at :1212 — reproduce exactly that end state.
-            out = self._forward_impl(images, exif_data, return_attention, keep_last=True)
-            if attention_guidance is not None:
-                B, S = self._check_images(images)
-                g = S // 14
-                ws = self._workspace(B, S)
-                ops.guided_softmax(ws["attn"][self.cfg.num_iterations - 1], self._mask(attention_guidance, g),
-                                   ws["heat"], ws["argmax"], B, g * g)
-                self._last_attention_weights = ws["heat"].clone()
-            return out
+            return self._forward_impl(images, exif_data, return_attention, mode="guided_fallback",
+                                      guidance=attention_guidance)
         B, S = self._check_images(images)
         pk = self._pack()
         dev = self._device()
@@ -524,7 +600,7 @@ class CognitiveAimModel(nn.Module):
         if mask.dim() == 2 and mask.shape[0] != B:
             raise ValueError(f"{mask.shape[0]} per-image instructions for a batch of {B}")
         exif, cam = self._exif_tensors(exif_data, B)
-        self._replay_reference_rng(B)
+        draws = [self._curiosity_draw(B)]  # :1185
         tmp = nn.Linear(_D, 64)  # same constructor => same CPU-generator draws as src/model.py:1421
         ws = self._workspace(B, S)
         # The projection travels through a small ring of PINNED staging buffers: a copy from pageable memory would block
@@ -532,74 +608,126 @@ class CognitiveAimModel(nn.Module):
         slot = self._pinned_slot()
         slot["w"].copy_(tmp.weight.detach())
         slot["b"].copy_(tmp.bias.detach())
+        self._stage_draws(ws, slot, draws)
         ws["mask_in"].copy_(mask, non_blocking=True)
         ws["tmpw"].copy_(slot["w"], non_blocking=True)
         ws["tmpb"].copy_(slot["b"], non_blocking=True)
         slot["event"].record()
-        tmp_w = tmp_b = None
         ws["exif_in"].copy_(exif, non_blocking=True)
         ws["cam_in"].copy_(cam, non_blocking=True)
         images = images.to(dev, torch.float32).contiguous()
         self._grid_tables(g)
         patches = ops.patchify_f32(images, ws["patches"])
+        cur_weight = ws["cur_weight"][0] if self.cfg.curiosity_guided else None
 
         def device_pass():
             self._backbone_layers(ws, patches, B, S)
-            base = self._focal_iterations(ws, B, g, want_features=False)
+            self._curiosity_runs(ws, B, T, ("guided",))
+            base = self._focal_iterations(ws, B, g, want_features=False, cur_weight=cur_weight)
             ops.guided_softmax(base, ws["mask_in"], ws["heat"], ws["argmax"], B, N)
             ops.weighted_pool(ws["tokens"], T * _D, 1, ws["heat"], None, ws["pool"], B, N, _D, _POOL_SPLITS)
             ops.heads(pk["heads"], tokens=ws["tokens"], tokens_per_img=T, depth=ws["depth"], conf=ws["conf"], B=B,
                       pool_partial=ws["pool"], pool_splits=_POOL_SPLITS, tmp_w=ws["tmpw"], tmp_b=ws["tmpb"],
                       pooled_out=ws["pooled"], exif=ws["exif_in"], camera_idx=ws["cam_in"])
 
-        self._run(ws, "guided", device_pass)
+        self._run(ws, ("guided", self._curiosity_key()), device_pass)
         # keep the temporaries referenced until the next call (their copies are enqueued, not finished)
-        self._keepalive = (tmp_w, tmp_b, exif, cam, mask, images)
+        self._keepalive = (exif, cam, mask, images)
         heat = ws["heat"].clone()
         self._last_attention_weights = heat  # :1212
         self._last_argmax = ws["argmax"].clone()
+        self._last_curiosity = ws["cur_reward"][0]
         depth, conf = ws["depth"].clone().unsqueeze(1), ws["conf"].clone().unsqueeze(1)
         return (depth, conf, heat) if return_attention else (depth, conf)
 
     @torch.no_grad()
     def forward(self, images, exif_data=None, return_attention=False):
         """reference src/model.py:1064-1155 (un-guided).  One backbone + one focal pass instead of 3 + 4."""
-        return self._forward_impl(images, exif_data, return_attention, keep_last=True)
+        return self._forward_impl(images, exif_data, return_attention, mode="forward")
 
-    def _forward_impl(self, images, exif_data, return_attention, keep_last):
+    def _forward_impl(self, images, exif_data, return_attention, mode, guidance=None):
+        """The un-guided paths.  `mode` selects which of the reference's entry points is being mirrored — they differ in
+        how often the CuriosityModule runs (RNG draws, ring-buffer entries) and in what `_last_attention_weights` ends as:
+          forward          get_features_aligned (:992) [+ :1104 when no `_last_attention_weights` is stored] [+ :1138 for
+                           return_attention]
+          features         get_features_aligned alone (:960-1048)
+          guided_none      forward_with_guidance(guidance=None) (:1185, :1206-1212): one run, attention always stored
+          guided_fallback  forward_with_guidance without EXIF: the guided attempt (:1185 [+ :1421 projection draws]) fails in
+                           `fusion` and falls back to forward() (:1237-1240) with the guided attention already stored."""
         B, S = self._check_images(images)
         pk = self._pack()
         g = S // 14
-        T = g * g + 1
+        N, T = g * g, g * g + 1
         exif, cam = self._exif_tensors(exif_data, B)
-        self._replay_reference_rng(B)
+        has_last = hasattr(self, "_last_attention_weights")
+        if mode == "forward":
+            roles = ["features"] + ([] if has_last else ["last"]) + (["ret"] if return_attention else [])
+        elif mode in ("features", "guided_none"):
+            roles = ["features"]
+        elif mode == "guided_fallback":
+            roles = ["guided", "features"] + (["ret"] if return_attention else [])
+        else:
+            raise AssertionError(mode)
+        mask = None
+        draws = []
+        for j, role in enumerate(roles):
+            draws.append(self._curiosity_draw(B))
+            if role == "guided" and guidance is not None:
+                mask = self._mask(guidance, g)
+                nn.Linear(_D, 64)  # :1421 is reached (and draws) before the 128-wide concat fails in `fusion`
         ws = self._workspace(B, S)
+        slot = self._pinned_slot()
+        self._stage_draws(ws, slot, draws)
+        slot["event"].record()
         has_exif = exif is not None
         if has_exif:
             ws["exif_in"].copy_(exif, non_blocking=True)
             ws["cam_in"].copy_(cam, non_blocking=True)
+        if mask is not None:
+            ws["mask_in"].copy_(mask, non_blocking=True)
         images = images.to(self._device(), torch.float32).contiguous()
         self._grid_tables(g)
         patches = ops.patchify_f32(images, ws["patches"])
+        cg = self.cfg.curiosity_guided
+        jf = roles.index("features")
 
         def device_pass():
             self._backbone_layers(ws, patches, B, S)
-            self._focal_iterations(ws, B, g, want_features=True)
+            self._curiosity_runs(ws, B, T, roles)
+            if cg:
+                # the attention-only calls of the reference see their own run's (clamped) score: separate passes
+                for j, role in enumerate(roles):
+                    if role != "features":
+                        att_j = self._focal_iterations(ws, B, g, want_features=False, cur_weight=ws["cur_weight"][j])
+                        ws["att_run"][j].copy_(att_j)
+            att_f = self._focal_iterations(ws, B, g, want_features=True, cur_weight=ws["cur_weight"][jf] if cg else None)
+            if mask is not None:
+                base = ws["att_run"][roles.index("guided")] if cg else att_f
+                ops.guided_softmax(base, ws["mask_in"], ws["heat"], ws["argmax"], B, N)
             ops.heads(pk["heads"], tokens=ws["tokens"], tokens_per_img=T, depth=ws["depth"], conf=ws["conf"], B=B,
                       focal_feat=ws["focal_feat"], exif=ws["exif_in"] if has_exif else None,
                       camera_idx=ws["cam_in"] if has_exif else None, fused_out=ws["fused"])
 
-        self._run(ws, ("unguided", has_exif), device_pass)
-        self._keepalive = (exif, cam, images)
-        att = ws["attn"][self.cfg.num_iterations - 1].clone()
+        self._run(ws, ("unguided", has_exif, tuple(roles), mask is not None, self._curiosity_key()), device_pass)
+        self._keepalive = (exif, cam, images, mask)
+        att_feat = ws["attn"][self.cfg.num_iterations - 1]
+
+        def att_of(role):
+            return (ws["att_run"][roles.index(role)] if cg and role != "features" else att_feat).clone()
+
         self.fusion_features = ws["fused"].clone()  # :1089
-        if keep_last:
-            if not hasattr(self, "_last_attention_weights"):  # :1093-1113 only set when absent
-                self._last_attention_weights = att
-        else:
-            self._last_attention_weights = att  # forward_with_guidance(..., guidance=None) always stores (:1212)
+        self._last_curiosity = ws["cur_reward"][jf]
+        if mode == "forward":
+            if not has_last:  # :1093-1113 only set when absent
+                self._last_attention_weights = att_of("last")
+        elif mode == "guided_none":
+            self._last_attention_weights = att_of("features")  # :1212 always stores
+        elif mode == "guided_fallback":
+            self._last_attention_weights = ws["heat"].clone() if mask is not None else att_of("guided")  # :1212
         depth, conf = ws["depth"].clone().unsqueeze(1), ws["conf"].clone().unsqueeze(1)
-        return (depth, conf, att) if return_attention else (depth, conf)
+        if not return_attention:
+            return depth, conf
+        return depth, conf, att_of("ret" if "ret" in roles else "features")
 
     # -- accessors ----------------------------------------------------------------------------------------
     def get_attention_weights(self):
@@ -609,7 +737,7 @@ class CognitiveAimModel(nn.Module):
     @torch.no_grad()
     def get_features_aligned(self, images, exif_data=None):
         """[B, 192] fused features (reference src/model.py:960-1048)."""
-        self._forward_impl(images, exif_data, False, keep_last=True)
+        self._forward_impl(images, exif_data, False, mode="features")
         return self.fusion_features
 
     def get_features(self, images, exif_data=None):

@@ -192,11 +192,15 @@ def colsum_e(E, wtab, pc, B, N):
     _end(e0, "colsum_e", 1, float(E.numel() * 2))
 
 
-def focal_finalize(pc, cbias, attn, rs_in, rs_out, B, N, focus_strength=1.5, mode=0):
+def focal_finalize(pc, cbias, attn, rs_in, rs_out, B, N, focus_strength=1.5, mode=0, cur_weight=None,
+                   adaptive_weight=0.5):
+    """cur_weight [B] (optional) + adaptive_weight: the curiosity modulation of src/model.py:264-276."""
     P = pc.shape[-1]
+    _req(cur_weight, torch.float32, "cur_weight")
     e0 = _begin()
     check(_lib.load().ca_focal_finalize(ptr(pc), ptr(cbias), ptr(attn), ptr(rs_in), ptr(rs_out), B, N, P,
-                                        float(focus_strength), mode, stream_ptr()), "ca_focal_finalize")
+                                        float(focus_strength), mode, ptr(cur_weight), float(adaptive_weight),
+                                        stream_ptr()), "ca_focal_finalize")
     _end(e0, "small", 1)
 
 
@@ -269,6 +273,58 @@ def heads(weights, *, tokens, tokens_per_img, depth, conf, B, focal_feat=None, p
     e0 = _begin()
     check(_lib.load().ca_heads(C.byref(weights), C.byref(inp), ptr(depth), ptr(conf), ptr(fused_out), B, stream_ptr()),
           "ca_heads")
+    _end(e0, "heads", 1)
+
+
+def make_curiosity_weights(named):
+    """named: dict field -> fp32 CUDA tensor or None for the four local_curiosity fields (kept alive by the caller)."""
+    w = _lib.CuriosityWeights()
+    for n in _lib.CuriosityWeights._names:
+        t = named.get(n)
+        _req(t, torch.float32, n)
+        setattr(w, n, None if t is None else t.data_ptr())
+    return w
+
+
+def make_curiosity_mod_weights(amp, mods):
+    """amp: (w0, b0, w1, b1) of curiosity_amplifier; mods: per iteration (w0, b0, w1, b1) of curiosity_modulator."""
+    w = _lib.CuriosityModWeights()
+    for n, t in zip(("amp_w0", "amp_b0", "amp_w1", "amp_b1"), amp):
+        _req(t, torch.float32, n)
+        setattr(w, n, t.data_ptr())
+    if len(mods) > 8:
+        raise ValueError("at most 8 focal iterations")
+    for i, four in enumerate(mods):
+        for n, t in zip(("mod_w0", "mod_b0", "mod_w1", "mod_b1"), four):
+            _req(t, torch.float32, n)
+            getattr(w, n)[i] = t.data_ptr()
+    return w
+
+
+def curiosity(weights, *, tokens, tokens_per_img, eps, noise, reward_raw, reward, history, history_pointer, B):
+    """CuriosityModule.forward on the CLS rows of `tokens` + the exploration ring-buffer update (csrc/curiosity.cu)."""
+    import ctypes as C
+    for t, n in ((tokens, "tokens"), (eps, "eps"), (noise, "noise"), (reward_raw, "reward_raw"), (reward, "reward"),
+                 (history, "history")):
+        _req(t, torch.float32, n)
+    _req(history_pointer, torch.int64, "history_pointer")
+    if eps.numel() < B * 192 or (noise is not None and noise.numel() < B * 768):
+        raise ValueError("eps / noise draws are smaller than the batch")
+    e0 = _begin()
+    check(_lib.load().ca_curiosity(C.byref(weights), ptr(tokens), tokens_per_img, ptr(eps), ptr(noise), ptr(reward_raw),
+                                   ptr(reward), ptr(history), 0 if history is None else history.numel(),
+                                   ptr(history_pointer), B, stream_ptr()), "ca_curiosity")
+    _end(e0, "heads", 1 if history is None else 2)
+
+
+def curiosity_modulation(weights, reward, lo, hi, cur_weight, B, n_iters, mod_hidden):
+    """cur_weight [n_iters, B]: head-mean modulator output per iteration (csrc/curiosity.cu); lo > hi = no clamp."""
+    import ctypes as C
+    _req(reward, torch.float32, "reward")
+    _req(cur_weight, torch.float32, "cur_weight")
+    e0 = _begin()
+    check(_lib.load().ca_curiosity_modulation(C.byref(weights), ptr(reward), float(lo), float(hi), ptr(cur_weight), B,
+                                              n_iters, mod_hidden, stream_ptr()), "ca_curiosity_modulation")
     _end(e0, "heads", 1)
 
 

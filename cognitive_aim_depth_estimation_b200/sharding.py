@@ -83,12 +83,14 @@ class ShardedInference:
         x, ex = shard_batch(images, exif_data, self.rank, self.world)
         if x.shape[0] == 0:
             raise ValueError(f"global batch of {n} leaves rank {self.rank} of {self.world} without images")
-        prev = getattr(self.model, "rng_replay_batch", None)
-        self.model.rng_replay_batch = n  # replay the reference's CPU-generator draws at the GLOBAL batch size
+        prev = (getattr(self.model, "rng_replay_batch", None), getattr(self.model, "rng_replay_offset", 0))
+        # replay the reference's CPU-generator draws at the GLOBAL batch size and use this shard's rows of them
+        self.model.rng_replay_batch = n
+        self.model.rng_replay_offset = shard_range(n, self.rank, self.world)[0]
         try:
             out = fn(x, ex, *args, **kw)
         finally:
-            self.model.rng_replay_batch = prev
+            self.model.rng_replay_batch, self.model.rng_replay_offset = prev
         if self.gather and self.world > 1:
             out = tuple(gather_outputs(list(out), n, self.group))
         return out

@@ -96,8 +96,11 @@ int ca_colsum_e(const uint16_t* E, int lde, long long e_batch_stride, const floa
 /* mode 0: FocalStream attention from CA_EPI_COLSUM partials: mean over rows + centre bias, L1 normalise, clamp 1e-8,
  *         renormalise; optionally rs_out = rs_in * (1 + focus_strength * attn)   (src/model.py:234-282, :426).
  * mode 1: attn = plain sum of the partials (weighted column sums of the un-guided value path). */
+/*         cur_weight (optional, [B]) with adaptive_weight: the curiosity modulation of src/model.py:264-276,
+ *         p <- aw * p * (1 + cur_weight[b]) + (1 - aw) * p between the L1 normalisation and the clamp. */
 int ca_focal_finalize(const float* pc, const float* cbias, float* attn, const float* rs_in, float* rs_out, int B, int N,
-                      int P, float focus_strength, int mode, void* stream);
+                      int P, float focus_strength, int mode, const float* cur_weight, float adaptive_weight,
+                      void* stream);
 /* heat = softmax((alpha*mask + (1-alpha)*base)/temperature) per image; argmax = first index of the maximum.
  * src/model.py:1404-1409.  mask_batch_stride = 0: one mask [N] for the whole batch (the reference broadcasts one
  * instruction per call, :1401); = N (or more): one mask per image, i.e. per-sample instructions in one batch
@@ -155,6 +158,44 @@ int ca_focal_value(const ca_focal_value_args* a, int B, void* stream);
 /* fused[B,64] = IterativeFocalStream.fusion(cat(feats))  (src/model.py:430); feats is [B, n_iters, 64]. */
 int ca_focal_fusion(const float* feats, int n_iters, const float* w0, const float* b0, const float* w1, const float* b1,
                     float* out, int B, void* stream);
+
+/* Curiosity module -------------------------------------------------------------------------------- */
+/* DEVICE pointers to the fp32 weights of reference `CuriosityModule` (src/model.py:524-583). */
+typedef struct ca_curiosity_weights {
+  const float *em_w0, *em_b0, *em_w1, *em_b1;     /* encoder_mean.{0,3}      [384,768] [192,384] */
+  const float *el_w0, *el_b0, *el_w1, *el_b1;     /* encoder_logvar.{0,3}    [384,768] [192,384] */
+  const float *dec_w0, *dec_b0, *dec_w1, *dec_b1; /* decoder.{0,3}           [384,192] [192,384] */
+  const float *unc_w0, *unc_b0, *unc_w1, *unc_b1; /* uncertainty_head.{0,2}  [192,768] [1,192] */
+  const float *loc_w0, *loc_b0, *loc_w1, *loc_b1; /* local_curiosity.{0,2}   [128,768] [1,128]; NULL = not hierarchical */
+  const float* cur_w;                             /* curiosity_weights [3] (geometric, local, variational) */
+} ca_curiosity_weights;
+
+/* CuriosityModule.forward(cls, exif_data=None) (src/model.py:586-688 with :690-700, :731-758): reward_raw[B] (before the
+ * final clamp; what the ring buffer records), reward[B] = clamp(reward_raw, 0, 100) (what callers get), and the
+ * sequential ring-buffer update history[ptr] = reward_raw[b]; ptr = (ptr + 1) % history_len for b = 0..B-1
+ * (src/model.py:760-773) on `history` / `history_pointer` (device int64) when `history` is not NULL.
+ * tokens: fp32 [B, tokens_per_img, 768], row 0 of each image is the CLS token.  eps [B,192] and noise [B,768] are the
+ * two standard-normal draws of :609 and :744, made by the caller (the reference takes them from the global generator).
+ * `w` is a HOST pointer. */
+int ca_curiosity(const ca_curiosity_weights* w, const float* tokens, int tokens_per_img, const float* eps,
+                 const float* noise, float* reward_raw, float* reward, float* history, int history_len,
+                 long long* history_pointer, int B, void* stream);
+
+/* DEVICE pointers to the curiosity-guided attention weights (only built when `curiosity_guided_attention.enabled`). */
+typedef struct ca_curiosity_mod_weights {
+  const float *amp_w0, *amp_b0, *amp_w1, *amp_b1; /* focal_stream.curiosity_amplifier.{0,2}  [32,1] [n_iters,32]  src/model.py:333-339 */
+  const float* mod_w0[8];                         /* focal_streams.{i}.curiosity_modulator.0 [32,1]   src/model.py:73-79 */
+  const float* mod_b0[8];
+  const float* mod_w1[8];                         /* focal_streams.{i}.curiosity_modulator.2 [8,32] */
+  const float* mod_b1[8];
+} ca_curiosity_mod_weights;
+
+/* cur_weight[i, b] = mean_h sigmoid(modulator_i(score_b * softmax(amplifier(score_b))[i]))  for i < n_iters <= 8, where
+ * score_b = clamp(reward[b], lo, hi)  (src/model.py:406-417, 266-269; the un-guided attention calls clamp the score to
+ * [0.5, 1], :1107, :1141; pass lo > hi for no clamp).  mod_hidden = focal_hidden_dim / 8 (<= 64), 8 modulator outputs.
+ * `w` is a HOST pointer. */
+int ca_curiosity_modulation(const ca_curiosity_mod_weights* w, const float* reward, float lo, float hi, float* cur_weight,
+                            int B, int n_iters, int mod_hidden, void* stream);
 
 /* ---- demo.py:162-163 `Resize((S, S))` on a PIL image = Pillow's antialiased bilinear resample, bit-exact ----------
  * src: uint8 [B, H0, W0, 3] (device), out: uint8 [B, out_h, out_w, 3].  tmp: uint8 [B, H0, out_w, 3] scratch, needed

@@ -45,19 +45,25 @@ def _xavier_u(lin: nn.Linear, gain: float):
 
 
 class _FocalInit(nn.Module):
-    """Parameter container with the construction + init order of FocalStream (src/model.py:58-126),
-    curiosity_guided=False (effective config)."""
+    """Parameter container with the construction + init order of FocalStream (src/model.py:58-126).
+    curiosity_guided=False is the effective config; True adds the modulator (:73-79)."""
 
-    def __init__(self, d=768, h=256):
+    def __init__(self, d=768, h=256, curiosity_guided=False):
         super().__init__()
         self.query_proj = nn.Linear(d, d)
         self.key_proj = nn.Linear(d, d)
         self.value_proj = nn.Linear(d, d)
+        if curiosity_guided:
+            self.curiosity_modulator = nn.Sequential(nn.Linear(1, h // 8), nn.ReLU(), nn.Linear(h // 8, 8), nn.Sigmoid())
         self.projection = nn.Sequential(nn.Linear(d, h), nn.ReLU(), nn.Dropout(0.1), nn.Linear(h, h // 4))
         self.adaptive_weight = nn.Parameter(torch.tensor(0.5))
         for m in self.projection:  # :98-103
             if isinstance(m, nn.Linear):
                 _xavier_u(m, 0.8)
+        if curiosity_guided:  # :106-111
+            for m in self.curiosity_modulator:
+                if isinstance(m, nn.Linear):
+                    _xavier_u(m, 0.8)
         with torch.no_grad():  # :114-126
             nn.init.xavier_normal_(self.query_proj.weight, gain=2.0)
             nn.init.xavier_normal_(self.key_proj.weight, gain=2.0)
@@ -68,16 +74,23 @@ class _FocalInit(nn.Module):
 
 
 class _IterFocalInit(nn.Module):
-    """IterativeFocalStream construction (src/model.py:318-389), curiosity_guided=False."""
+    """IterativeFocalStream construction (src/model.py:318-389)."""
 
-    def __init__(self, d=768, h=256, iters=3):
+    def __init__(self, d=768, h=256, iters=3, curiosity_guided=False):
         super().__init__()
-        self.focal_streams = nn.ModuleList([_FocalInit(d, h) for _ in range(iters)])
+        self.focal_streams = nn.ModuleList([_FocalInit(d, h, curiosity_guided) for _ in range(iters)])
         self.initial_focus = nn.Parameter(torch.randn(1, d))
+        if curiosity_guided:  # :333-339
+            self.curiosity_amplifier = nn.Sequential(nn.Linear(1, 32), nn.ReLU(), nn.Linear(32, iters),
+                                                     nn.Softmax(dim=-1))
         self.fusion = nn.Sequential(nn.Linear(h // 4 * iters, h // 2), nn.ReLU(), nn.Linear(h // 2, h // 4))
         for m in self.fusion:  # :354-358
             if isinstance(m, nn.Linear):
                 _xavier_u(m, 0.8)
+        if curiosity_guided:  # :361-366
+            for m in self.curiosity_amplifier:
+                if isinstance(m, nn.Linear):
+                    _xavier_u(m, 0.8)
         nn.init.normal_(self.initial_focus, mean=0.0, std=0.02)  # :369
         for i, fs in enumerate(self.focal_streams):  # :372-389
             with torch.no_grad():
@@ -118,14 +131,14 @@ class _CuriosityInit(nn.Module):  # CuriosityModule.__init__, src/model.py:524-5
 class _ModelInit(nn.Module):
     """Construction order of CognitiveAimModel.__init__ (src/model.py:798-958) under the effective config."""
 
-    def __init__(self, num_cameras=71):
+    def __init__(self, num_cameras=71, curiosity_guided=False):
         super().__init__()
         from transformers import Dinov2Config, Dinov2Model  # the reference's own backbone dependency
         self.backbone = Dinov2Model(Dinov2Config(image_size=518, patch_size=14))  # :814 (offline: random init)
         self.ambient_stream = nn.Module()
         self.ambient_stream.mlp = nn.Sequential(nn.Linear(768, 256), nn.ReLU(), nn.Dropout(0.1), nn.Linear(256, 128),
                                                 nn.ReLU(), nn.Linear(128, 64))  # :37-44
-        self.focal_stream = _IterFocalInit(768, 256, 3)  # :857-864
+        self.focal_stream = _IterFocalInit(768, 256, 3, curiosity_guided)  # :857-864
         ex = nn.Module()  # EXIFPriorDatabase :460-480
         ex.camera_embedding = nn.Embedding(num_cameras, 64)
         ex.exif_encoder = nn.Sequential(nn.Linear(3, 64), nn.ReLU(), nn.Linear(64, 64))
@@ -146,11 +159,12 @@ class _ModelInit(nn.Module):
         self.global_aligner = _AlignerInit(768, 768 * 3)  # :958
 
 
-def build_state_dict(seed: int = 0, num_cameras: int = 71) -> SD:
+def build_state_dict(seed: int = 0, num_cameras: int = 71, curiosity_guided: bool = False) -> SD:
     """`torch.manual_seed(seed); create_model(cfg, {'num_cameras': 71}).state_dict()` of the reference
-    (SURVEY.md §8c seed protocol), without the reference."""
+    (SURVEY.md §8c seed protocol), without the reference.  curiosity_guided=True is what a config with the top-level
+    key `curiosity_guided_attention: {enabled: true}` builds (src/model.py:854): 16 more tensors."""
     torch.manual_seed(seed)
-    m = _ModelInit(num_cameras).eval()
+    m = _ModelInit(num_cameras, curiosity_guided).eval()
     return {k: v.detach().clone() for k, v in m.state_dict().items()}
 
 
@@ -259,9 +273,9 @@ def _mlp(sd: SD, x, names, relu_last=False):
     return x
 
 
-def focal_stream(sd: SD, prefix: str, tokens: torch.Tensor, need_features: bool = True):
-    """One FocalStream.forward (src/model.py:128-313), curiosity_guided=False.
-    Returns (features [B,64] or None, attention [B,N])."""
+def focal_stream(sd: SD, prefix: str, tokens: torch.Tensor, need_features: bool = True, curiosity_score=None):
+    """One FocalStream.forward (src/model.py:128-313).  `curiosity_score` [B] is used only when the state dict holds a
+    curiosity_modulator (curiosity_guided=True, :264-276).  Returns (features [B,64] or None, attention [B,N])."""
     B, N, D = tokens.shape
     x = tokens + focal_position_encoding(N, D).unsqueeze(0)  # :184
     q = F.linear(x, sd[prefix + "query_proj.weight"], sd[prefix + "query_proj.bias"])
@@ -277,6 +291,12 @@ def focal_stream(sd: SD, prefix: str, tokens: torch.Tensor, need_features: bool 
         norms = x.norm(dim=-1)
         pa = norms + torch.randn_like(norms) * 0.1 * norms.std()
     pa = pa / (pa.sum(dim=-1, keepdim=True) + 1e-8)  # :261
+    if prefix + "curiosity_modulator.0.weight" in sd and curiosity_score is not None:  # :264-276
+        mod = torch.sigmoid(_mlp(sd, curiosity_score.unsqueeze(-1),
+                                 [prefix + "curiosity_modulator.0", prefix + "curiosity_modulator.2"]))
+        cw = mod.mean(dim=-1, keepdim=True)
+        aw = sd[prefix + "adaptive_weight"]
+        pa = aw * (pa * (1.0 + cw)) + (1 - aw) * pa
     pa = pa.clamp(min=1e-8)  # :281-282
     pa = pa / (pa.sum(dim=-1, keepdim=True) + 1e-8)
     feats = None
@@ -288,13 +308,18 @@ def focal_stream(sd: SD, prefix: str, tokens: torch.Tensor, need_features: bool 
 
 
 def iterative_focal_stream(sd: SD, tokens: torch.Tensor, need_features: bool = True, iters: int = 3,
-                           focus_strength: float = 1.5, prefix: str = "focal_stream."):
+                           focus_strength: float = 1.5, prefix: str = "focal_stream.", curiosity_score=None):
     """IterativeFocalStream.forward (src/model.py:391-455). Returns (fused [B,64] or None, last attention [B,N])."""
     cur = tokens
     feats = []
     att = None
+    iter_w = None
+    if prefix + "curiosity_amplifier.0.weight" in sd and curiosity_score is not None:  # :406-409
+        iter_w = torch.softmax(_mlp(sd, curiosity_score.unsqueeze(-1),
+                                    [prefix + "curiosity_amplifier.0", prefix + "curiosity_amplifier.2"]), dim=-1)
     for i in range(iters):
-        f, att = focal_stream(sd, f"{prefix}focal_streams.{i}.", cur, need_features)
+        sc = curiosity_score * iter_w[:, i] if iter_w is not None else curiosity_score  # :412-417
+        f, att = focal_stream(sd, f"{prefix}focal_streams.{i}.", cur, need_features, sc)
         feats.append(f)
         if i < iters - 1:
             cur = cur * (1 + focus_strength * att.unsqueeze(-1))  # :426
@@ -413,9 +438,10 @@ def forward_with_guidance(sd: SD, images: torch.Tensor, exif: Optional[dict], gu
     if tokens is None:
         tokens = dinov2_tokens(sd, images)
     cls, patches = tokens[:, 0], tokens[:, 1:]
-    curiosity_module(sd, cls, update_history)  # :1185 (result unused: curiosity_guided=False)
+    score = curiosity_module(sd, cls, update_history)  # :1185 (only consumed when curiosity_guided=True)
     amb = ambient_stream(sd, cls)  # :1196
-    _, base = iterative_focal_stream(sd, patches, need_features=False)  # :1257 (features discarded at :1424)
+    _, base = iterative_focal_stream(sd, patches, need_features=False,
+                                     curiosity_score=score)  # :1257 (features discarded at :1424)
     g = resolve_guidance(guidance, patches.size(1))
     guided = torch.softmax((0.7 * g.unsqueeze(0) + 0.3 * base) / 0.05, dim=-1)  # :1404-1409
     pooled = (patches * guided.unsqueeze(-1)).sum(dim=1)  # :1412-1414
@@ -424,19 +450,29 @@ def forward_with_guidance(sd: SD, images: torch.Tensor, exif: Optional[dict], gu
     ex = exif_prior(sd, exif)  # :1216
     depth, conf, _ = heads(sd, torch.cat([amb, focal, ex], dim=1))
     return {"depth": depth, "confidence": conf, "heatmap": guided, "base_attention": base, "pooled": pooled,
-            "tokens": tokens}
+            "tokens": tokens, "curiosity": score}
 
 
 @torch.no_grad()
-def forward_unguided(sd: SD, images: torch.Tensor, exif: Optional[dict], tokens=None, update_history: bool = True):
-    """CognitiveAimModel.forward(images, exif, return_attention=True) (src/model.py:1064-1155): identical
-    repeated backbone / focal passes of the reference are computed once (they are bit-identical in eval)."""
+def forward_unguided(sd: SD, images: torch.Tensor, exif: Optional[dict], tokens=None, update_history: bool = True,
+                     has_last_attention: bool = False, return_attention: bool = True):
+    """CognitiveAimModel.forward(images, exif, return_attention) (src/model.py:1064-1155): identical repeated backbone
+    passes of the reference are computed once (they are bit-identical in eval).  The CuriosityModule runs once in
+    get_features_aligned (:992), once more when the model holds no `_last_attention_weights` (:1093-1104,
+    `has_last_attention=False`) and once more for return_attention (:1138) — each run draws fresh noise and appends B
+    rewards to the exploration ring buffer.  With curiosity_guided=True the features use the first score un-clamped and
+    the returned attention the last score clamped to [0.5, 1] (:1107, :1141)."""
     if tokens is None:
         tokens = dinov2_tokens(sd, images)
     cls, patches = tokens[:, 0], tokens[:, 1:]
-    curiosity_module(sd, cls, update_history)
+    score = curiosity_module(sd, cls, update_history)
     amb = ambient_stream(sd, cls)
-    fused, att = iterative_focal_stream(sd, patches, need_features=True)
+    fused, att = iterative_focal_stream(sd, patches, need_features=True, curiosity_score=score)
+    guided_cfg = "focal_stream.curiosity_amplifier.0.weight" in sd
+    for extra in ([] if has_last_attention else ["last"]) + (["ret"] if return_attention else []):
+        sc = curiosity_module(sd, cls, update_history).clamp(0.5, 1.0)
+        if guided_cfg and extra == "ret":
+            _, att = iterative_focal_stream(sd, patches, need_features=False, curiosity_score=sc)
     parts = [amb, fused]
     if exif is not None:
         parts.append(exif_prior(sd, exif))

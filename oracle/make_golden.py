@@ -5,7 +5,8 @@ network access at reference src/model.py:814 (`Dinov2Model.from_pretrained`) -> 
 `Dinov2Model(Dinov2Config(image_size=518, patch_size=14))`.  Seed protocol: weights
 `torch.manual_seed(0)`; images seed 1234; EXIF seed 1236; `torch.manual_seed(11)` before every call.
 
-    python oracle/make_golden.py            # writes tests/golden/*.npz / *.json
+    python oracle/make_golden.py                    # writes tests/golden/*.npz / *.json
+    python oracle/make_golden.py --only-curiosity   # only curiosity.npz / curiosity_guided.npz (sections 6-7)
 """
 from __future__ import annotations
 
@@ -38,8 +39,9 @@ def load_reference():
     return ref
 
 
-def make_model(ref, cfg_path):
+def make_model(ref, cfg_path, extra=None):
     cfg = yaml.safe_load(open(cfg_path))
+    cfg.update(extra or {})
     cfg.setdefault("cognitive_modules", ["ambient_stream", "iterative_focal_stream", "exif_prior_database"])  # demo.py:46-52
     torch.manual_seed(WEIGHT_SEED)
     with contextlib.redirect_stdout(io.StringIO()):
@@ -60,10 +62,85 @@ def effective_attrs(model):
     }
 
 
+def curiosity_sections(ref):
+    """6. CuriosityModule side effects (rewards, exploration ring buffer, pointer) over a sequence of calls, and
+    7. the curiosity-guided configuration (top-level `curiosity_guided_attention.enabled`, src/model.py:854)."""
+    cfg_path = os.path.join(REF, "configs", "experiment_B.yaml")
+    S, B = 224, 2
+    x, ex = orc.synthetic_images(B, S), orc.synthetic_exif(B)
+
+    def run_sequence(model, out, tag):
+        rewards = []
+        hook = model.curiosity_module.register_forward_hook(lambda m, i, o: rewards.append(o[0].detach().clone()))
+        cm = model.curiosity_module
+
+        def snap(step):
+            out[f"{tag}{step}_history"] = cm.exploration_history[:32].numpy().copy()
+            out[f"{tag}{step}_history_tail"] = cm.exploration_history[-4:].numpy().copy()
+            out[f"{tag}{step}_pointer"] = np.asarray(int(cm.history_pointer))
+            out[f"{tag}{step}_rewards"] = torch.stack(rewards).numpy() if rewards else np.zeros((0, B), np.float32)
+            rewards.clear()
+
+        def call(fn, *a, **k):
+            torch.manual_seed(CALL_SEED)
+            with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+                return fn(*a, **k)
+
+        if hasattr(model, "_last_attention_weights"):
+            delattr(model, "_last_attention_weights")
+        d, c, h = call(model.forward_with_guidance, x, ex, "center", return_attention=True)   # 1 curiosity run
+        out[f"{tag}1_depth"], out[f"{tag}1_heat"] = d.numpy(), h.numpy()
+        snap(1)
+        d, c, h = call(model, x, ex, return_attention=True)      # _last_attention_weights present: 2 runs
+        out[f"{tag}2_depth"], out[f"{tag}2_heat"], out[f"{tag}2_fusion"] = d.numpy(), h.numpy(), model.fusion_features.numpy()
+        snap(2)
+        delattr(model, "_last_attention_weights")
+        d, c, h = call(model, x, None, return_attention=True)    # absent: 3 runs
+        out[f"{tag}3_depth"], out[f"{tag}3_heat"] = d.numpy(), h.numpy()
+        snap(3)
+        call(model, x, ex)                                       # present, no attention: 1 run
+        snap(4)
+        d, c, h = call(model.forward_with_guidance, x, None, "left", return_attention=True)   # guided attempt + fallback
+        out[f"{tag}5_depth"], out[f"{tag}5_heat"] = d.numpy(), h.numpy()
+        out[f"{tag}5_last_attention"] = model._last_attention_weights.numpy()
+        snap(5)
+        cm.history_pointer.fill_(999)                            # wrap-around of the ring buffer
+        call(model.forward_with_guidance, x, ex, "top", return_attention=True)
+        snap(6)
+        hook.remove()
+
+    out = {}
+    run_sequence(make_model(ref, cfg_path), out, "seq")
+    np.savez_compressed(os.path.join(OUT, "curiosity.npz"), **out)
+    for k in sorted(out):
+        if k.endswith("_pointer") or k.endswith("_rewards"):
+            print(k, out[k].ravel())
+
+    out = {}
+    model = make_model(ref, cfg_path, {"curiosity_guided_attention": {"enabled": True}})
+    assert model.focal_stream.curiosity_guided
+    sd = model.state_dict()
+    json.dump({"seed": WEIGHT_SEED, "names": list(sd.keys()), "shapes": {k: list(v.shape) for k, v in sd.items()},
+               "digest": orc.state_dict_digest(sd)}, open(os.path.join(OUT, "state_dict_seed0_curiosity_guided.json"), "w"))
+    run_sequence(model, out, "seq")
+    for ins in ("top-left", "right"):
+        if hasattr(model, "_last_attention_weights"):
+            delattr(model, "_last_attention_weights")
+        torch.manual_seed(CALL_SEED)
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            d, c, h = model.forward_with_guidance(x, ex, ins, return_attention=True)
+        out[f"guided_{ins}_depth"], out[f"guided_{ins}_conf"], out[f"guided_{ins}_heat"] = d.numpy(), c.numpy(), h.numpy()
+    np.savez_compressed(os.path.join(OUT, "curiosity_guided.npz"), **out)
+    print("curiosity-guided: state tensors", len(sd))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
     torch.set_num_threads(os.cpu_count())
+    if "--only-curiosity" in sys.argv:
+        curiosity_sections(ref)
+        return
 
     # 1. effective config of every shipped YAML (quirk 1) ------------------------------------------------
     attrs = {}
@@ -137,6 +214,7 @@ def main():
         out[f"S{S}_B{B}_tokens_tail"] = t[:, -4:, -32:].numpy()
         out[f"S{S}_B{B}_token_norms"] = t.norm(dim=-1).numpy()
     np.savez_compressed(os.path.join(OUT, "backbone.npz"), **out)
+    curiosity_sections(ref)
     print("golden vectors written to", OUT)
 
 

@@ -91,7 +91,18 @@ def test_unsupported_configs_raise():
         CognitiveAimModel({"cognitive_modules": ["ambient_stream"]}, {"num_cameras": 71})
     with pytest.raises(NotImplementedError):
         CognitiveAimModel({"cognitive_modules": ["ambient_stream", "iterative_focal_stream"],
-                           "curiosity_guided_attention": {"enabled": True}}, None)
+                           "focal_config": {"num_iterations": 9}}, None)
+
+
+def test_curiosity_guided_state_dict_is_reference_compatible():
+    """Top-level `curiosity_guided_attention: {enabled: true}` (src/model.py:854) adds the modulators and the amplifier:
+    the reference's 335 names / shapes, in its order."""
+    gold = json.load(open(os.path.join(GOLD, "state_dict_seed0_curiosity_guided.json")))
+    m = create_model(dict(SHIPPED_LIKE, curiosity_guided_attention={"enabled": True}), {"num_cameras": 71})
+    sd = m.state_dict()
+    assert list(sd.keys()) == gold["names"] and len(sd) == 335
+    for k, v in sd.items():
+        assert list(v.shape) == gold["shapes"][k], k
 
 
 def test_tables_match_oracle_definitions():

@@ -133,3 +133,90 @@ def test_focus_map_restatement_shapes_and_range():
     assert abs(float(grid.max()) - 1.0) < 1e-4 and float(grid.min()) == 0.0  # (max - min) / (max - min + 1e-8)
     # 70 % of the cubed cells sit at or below the percentile threshold and were scaled by 0.3
     assert 0.6 < float((grid < grid.flatten(1).quantile(0.7, dim=1).view(2, 1, 1) + 1e-9).float().mean()) < 0.8
+
+
+# --- CuriosityModule side effects and the curiosity-guided configuration (tests/golden/curiosity*.npz) -------------------
+
+def _curiosity_sequence(sd, tokens, gold, check_outputs):
+    """Replays oracle/make_golden.py `run_sequence` on the oracle; compares rewards, ring buffer and pointer per step."""
+    ex = orc.synthetic_exif(2)
+    p = "curiosity_module."
+    sd[p + "exploration_history"] = torch.zeros(1000)
+    sd[p + "history_pointer"] = torch.tensor(0)
+
+    def check(step, rewards):
+        np.testing.assert_allclose(torch.stack(rewards).numpy(), gold[f"seq{step}_rewards"], rtol=2e-5)
+        np.testing.assert_allclose(sd[p + "exploration_history"][:32].numpy(), gold[f"seq{step}_history"], rtol=2e-5)
+        np.testing.assert_allclose(sd[p + "exploration_history"][-4:].numpy(), gold[f"seq{step}_history_tail"], rtol=2e-5)
+        assert int(sd[p + "history_pointer"]) == int(gold[f"seq{step}_pointer"])
+
+    rewards = []
+    real = orc.curiosity_module
+
+    def spy(*a, **k):
+        r = real(*a, **k)
+        rewards.append(r.clone())
+        return r
+
+    orc.curiosity_module = spy
+    try:
+        torch.manual_seed(11)
+        o = orc.forward_with_guidance(sd, None, ex, "center", tokens=tokens)
+        check(1, rewards)
+        if check_outputs:
+            np.testing.assert_allclose(o["depth"].numpy(), gold["seq1_depth"], rtol=2e-5)
+            np.testing.assert_allclose(o["heatmap"].numpy(), gold["seq1_heat"], rtol=2e-3, atol=1e-9)
+        rewards.clear()
+        torch.manual_seed(11)
+        o = orc.forward_unguided(sd, None, ex, tokens=tokens, has_last_attention=True)
+        check(2, rewards)
+        if check_outputs:
+            np.testing.assert_allclose(o["depth"].numpy(), gold["seq2_depth"], rtol=2e-5)
+            np.testing.assert_allclose(o["heatmap"].numpy(), gold["seq2_heat"], rtol=2e-3, atol=1e-9)
+            np.testing.assert_allclose(o["fusion_features"].numpy(), gold["seq2_fusion"], rtol=1e-4, atol=1e-6)
+        rewards.clear()
+        torch.manual_seed(11)
+        o = orc.forward_unguided(sd, None, None, tokens=tokens, has_last_attention=False)
+        check(3, rewards)
+        if check_outputs:
+            np.testing.assert_allclose(o["depth"].numpy(), gold["seq3_depth"], rtol=2e-5)
+            np.testing.assert_allclose(o["heatmap"].numpy(), gold["seq3_heat"], rtol=2e-3, atol=1e-9)
+        rewards.clear()
+        torch.manual_seed(11)
+        orc.forward_unguided(sd, None, ex, tokens=tokens, has_last_attention=True, return_attention=False)
+        check(4, rewards)
+    finally:
+        orc.curiosity_module = real
+
+
+def test_curiosity_rewards_and_ring_buffer(sd, tokens224):
+    gold = np.load(os.path.join(GOLD, "curiosity.npz"))
+    _curiosity_sequence(dict(sd), tokens224, gold, check_outputs=False)
+    # ring-buffer wrap-around: pointer 999 + 2 rewards -> slots 999, 0; pointer 1   (src/model.py:770-773)
+    s2 = dict(sd)
+    s2["curiosity_module.exploration_history"] = torch.zeros(1000)
+    s2["curiosity_module.history_pointer"] = torch.tensor(999)
+    torch.manual_seed(11)
+    orc.forward_with_guidance(s2, None, orc.synthetic_exif(2), "top", tokens=tokens224)
+    assert int(s2["curiosity_module.history_pointer"]) == int(gold["seq6_pointer"]) == 1
+    np.testing.assert_allclose(s2["curiosity_module.exploration_history"][-1].item(), gold["seq6_history_tail"][-1], rtol=2e-5)
+    np.testing.assert_allclose(s2["curiosity_module.exploration_history"][0].item(), gold["seq6_history"][0], rtol=2e-5)
+
+
+def test_curiosity_guided_state_dict_and_forward():
+    """Top-level `curiosity_guided_attention: {enabled: true}` (src/model.py:854): 335 tensors, modulated attention."""
+    gold_sd = json.load(open(os.path.join(GOLD, "state_dict_seed0_curiosity_guided.json")))
+    sd = orc.build_state_dict(0, curiosity_guided=True)
+    assert list(sd.keys()) == gold_sd["names"] and len(sd) == 335
+    for k, v in sd.items():
+        s, a = gold_sd["digest"][k]
+        assert float(v.double().sum()) == s and float(v.double().abs().sum()) == a, k
+    tokens = orc.dinov2_tokens(sd, orc.synthetic_images(2, 224))
+    gold = np.load(os.path.join(GOLD, "curiosity_guided.npz"))
+    _curiosity_sequence(dict(sd), tokens, gold, check_outputs=True)
+    for ins in ("top-left", "right"):
+        torch.manual_seed(11)
+        o = orc.forward_with_guidance(dict(sd), None, orc.synthetic_exif(2), ins, tokens=tokens)
+        np.testing.assert_allclose(o["depth"].numpy(), gold[f"guided_{ins}_depth"], rtol=2e-5)
+        np.testing.assert_allclose(o["heatmap"].numpy(), gold[f"guided_{ins}_heat"], rtol=2e-3, atol=1e-9)
+        assert (o["heatmap"].argmax(-1).numpy() == gold[f"guided_{ins}_heat"].argmax(-1)).all()

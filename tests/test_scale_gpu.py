@@ -28,13 +28,13 @@ def _exif(ex, lo=None, hi=None):
     return {k: v[lo:hi].cuda() for k, v in ex.items()}
 
 
-def _guided(model, x, ex, instruction, replay_batch=None):
+def _guided(model, x, ex, instruction, replay_batch=None, replay_offset=0):
     torch.manual_seed(11)
-    model.rng_replay_batch = replay_batch
+    model.rng_replay_batch, model.rng_replay_offset = replay_batch, replay_offset
     try:
         out = model.forward_with_guidance(x, ex, instruction, return_attention=True)
     finally:
-        model.rng_replay_batch = None
+        model.rng_replay_batch, model.rng_replay_offset = None, 0
     return [t.clone() for t in out]
 
 
@@ -50,7 +50,7 @@ def test_full_batch_properties_and_batch_invariance(model):
     assert (depth > 0).all() and ((conf > 0) & (conf < 1)).all()
     assert torch.allclose(heat.sum(-1), torch.ones(B, device=heat.device), atol=1e-5)
     for lo in (0, 14, 30):
-        d2, c2, h2 = _guided(model, x[lo:lo + 2], _exif(ex, lo, lo + 2), "bottom-right", replay_batch=B)
+        d2, c2, h2 = _guided(model, x[lo:lo + 2], _exif(ex, lo, lo + 2), "bottom-right", replay_batch=B, replay_offset=lo)
         assert torch.equal(d2, depth[lo:lo + 2]) and torch.equal(c2, conf[lo:lo + 2]) and torch.equal(h2, heat[lo:lo + 2])
 
 

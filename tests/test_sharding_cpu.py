@@ -47,14 +47,17 @@ def test_rng_replay_uses_global_batch():
     torch.randn(8, 192)
     torch.randn(8, 768)
     want = nn.Linear(768, 64)
-    m.rng_replay_batch = 8
+    m.rng_replay_batch, m.rng_replay_offset = 8, 4
     torch.manual_seed(11)
-    m._replay_reference_rng(4)
+    eps, noise = m._curiosity_draw(4)
     got = nn.Linear(768, 64)
     assert torch.equal(got.weight, want.weight) and torch.equal(got.bias, want.bias)
-    m.rng_replay_batch = None
+    # ... and the shard's CuriosityModule sees ITS rows of the global draws (src/model.py:609,744)
     torch.manual_seed(11)
-    m._replay_reference_rng(4)
+    assert torch.equal(eps, torch.randn(8, 192)[4:8]) and torch.equal(noise, torch.randn(8, 768)[4:8])
+    m.rng_replay_batch, m.rng_replay_offset = None, 0
+    torch.manual_seed(11)
+    m._curiosity_draw(4)
     other = nn.Linear(768, 64)
     assert not torch.equal(other.weight, want.weight)
 
@@ -63,6 +66,7 @@ class _HostOnlyModel:
     """Stands in for the CUDA model in the gloo test: same host protocol (rng_replay_batch, per-call projection from
     the CPU generator, per-image outputs), trivial per-image arithmetic."""
     rng_replay_batch = None
+    rng_replay_offset = 0
 
     def forward_with_guidance(self, images, exif_data=None, attention_guidance=None, return_attention=False):
         B = self.rng_replay_batch or images.shape[0]
@@ -99,7 +103,7 @@ def _worker(rank, world, port, n, out_dir):
         runner = sharding.ShardedInference(model, rank, world, gather=True)
         torch.manual_seed(11)
         got = runner.forward_with_guidance(x, ex, "center", return_attention=True)
-        assert model.rng_replay_batch is None
+        assert model.rng_replay_batch is None and model.rng_replay_offset == 0
         ok = all(torch.equal(a, b) for a, b in zip(got, want)) and got[2].shape == (n, 16)
         # local-only mode returns just this rank's rows
         lo, hi = sharding.shard_range(n, rank, world)

@@ -6,7 +6,8 @@ from cognitive_aim_depth_estimation_b200 import ops
 M = 32 * 1370
 dev = 'cuda'
 shapes = [("qkv", 2304, 768, ops.EPI_BIAS_BF16), ("proj", 768, 768, ops.EPI_RESID_F32),
-          ("fc1", 3072, 768, ops.EPI_GELU_BF16), ("fc2", 768, 3072, ops.EPI_RESID_F32)]
+          ("fc1", 3072, 768, ops.EPI_GELU_BF16), ("fc1-nogelu", 3072, 768, ops.EPI_BIAS_BF16),
+          ("fc2", 768, 3072, ops.EPI_RESID_F32), ("focal-qk", 1536, 768, ops.EPI_BIAS_BF16)]
 for name, N, K, epi in shapes:
     A = torch.randn(M, K, device=dev).bfloat16()
     W = (torch.randn(N, K, device=dev) * 0.02).bfloat16()
@@ -23,4 +24,4 @@ for name, N, K, epi in shapes:
         e0.record(); ops.gemm(A, W, epi, out, bias=bias, ls=ls); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     t = sorted(ts)[len(ts) // 2]
-    print(f"{name:5s} N={N:5d} K={K:5d}  {t*1e3:8.1f} us  {2*M*N*K/t/1e9:8.1f} TF/s")
+    print(f"{name:10s} N={N:5d} K={K:5d}  {t*1e3:8.1f} us  {2*M*N*K/t/1e9:8.1f} TF/s")
