@@ -30,6 +30,7 @@ class EffectiveConfig:
     focus_strength: float
     focal_hidden_dim: int
     enable_hierarchical_curiosity: bool
+    lora_merge_target: Optional[str] = None  # NOT a reference key: see model.CognitiveAimModel._lora_delta
     fusion_dim: int = 192  # src/model.py:904-905
 
 
@@ -58,4 +59,5 @@ def effective_config(config: dict, camera_info: Optional[dict] = None) -> Effect
         focus_strength=float(focal_cfg.get("focus_strength", 1.5)),  # :862
         focal_hidden_dim=int(config.get("focal_hidden_dim", 256)),  # :859
         enable_hierarchical_curiosity=bool(config.get("enable_hierarchical_curiosity", True)),  # :951
+        lora_merge_target=config.get("lora_merge_target"),
     )

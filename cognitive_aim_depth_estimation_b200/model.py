@@ -62,6 +62,9 @@ def _param_specs(cfg: EffectiveConfig):
               (p + "mlp.fc2.weight", (_D, _MLP), "w"), (p + "mlp.fc2.bias", (_D,), "zeros"),
               (p + "layer_scale2.lambda1", (_D,), "ones")]
     s += [("backbone.layernorm.weight", (_D,), "ones"), ("backbone.layernorm.bias", (_D,), "zeros")]
+    if cfg.use_lora:  # src/model.py:822-831: one LoRALayer(768, 768, rank) per encoder layer, lora_B zero-initialised
+        for i in range(_LAYERS):
+            s += [(f"lora_layers.{i}.lora_A", (cfg.lora_rank, _D), "w"), (f"lora_layers.{i}.lora_B", (_D, cfg.lora_rank), "zeros")]
 
     def lin(name, o, i):
         return [(name + ".weight", (o, i), "w"), (name + ".bias", (o,), "zeros")]
@@ -137,7 +140,13 @@ class CognitiveAimModel(nn.Module):
         self.backbone_size = cfg.backbone_size
         self.feature_dim = cfg.feature_dim
         self.fusion_dim = cfg.fusion_dim
-        self.use_lora = cfg.use_lora  # LoRA is dead code in the reference (quirk 4): flag kept, nothing executed
+        # LoRA is dead code in the reference (quirk 4): `lora_layers` are built and saved, never applied.  Same here,
+        # unless the NON-reference key `lora_merge_target` asks for the adapters to be merged into a weight (_lora_delta).
+        self.use_lora = cfg.use_lora
+        if cfg.lora_merge_target not in (None, "query", "key", "value", "attention_output"):
+            raise ValueError("lora_merge_target must be one of query / key / value / attention_output")
+        if cfg.lora_merge_target and not cfg.use_lora:
+            raise ValueError("lora_merge_target needs use_lora: true")
         self.use_ambient, self.use_focal = cfg.use_ambient, cfg.use_focal
         self.use_iterative, self.use_exif = cfg.use_iterative, cfg.use_exif
         self.target_fusion_dim = 768
@@ -196,6 +205,22 @@ class CognitiveAimModel(nn.Module):
         return dict(self.state_dict(keep_vars=True))
 
     # -- weight packing ---------------------------------------------------------------------------------
+    def _lora_delta(self, sd, layer: int, target: str):
+        """(alpha / rank) * lora_B @ lora_A of encoder layer `layer` when `lora_merge_target == target`, else None.
+
+        The reference constructs one LoRALayer(768, 768, rank, alpha=16) per encoder layer (src/model.py:15-24, 822-831) and
+        never applies it (its forward calls a non-existent `lora_projection`, :30), so the reference-faithful behaviour —
+        the default here — is that LoRA parameters travel in the state_dict and change nothing.  For a deployment that
+        does want y = W x + (alpha/rank) B A x on one of the 768 -> 768 projections, the adapters are MERGED into that
+        projection's weight when the bf16 operands are packed: on an inference path with one adapter set this is
+        exactly the LoRA output at zero extra HBM traffic, FLOPs or launches, which no epilogue-fused rank-16 MMA step
+        can beat (that form only pays when adapters change per request, which the reference cannot express)."""
+        if not self.cfg.use_lora or self.cfg.lora_merge_target != target:
+            return None
+        A = sd[f"lora_layers.{layer}.lora_A"].float()
+        Bm = sd[f"lora_layers.{layer}.lora_B"].float()
+        return (16.0 / self.cfg.lora_rank) * (Bm @ A)  # alpha defaults to 16 (:15), scaling = alpha / rank (:19)
+
     def _device(self) -> torch.device:
         return self.backbone.layernorm.weight.device
 
@@ -220,11 +245,17 @@ class CognitiveAimModel(nn.Module):
         for i in range(_LAYERS):
             p = f"backbone.encoder.layer.{i}."
             a = p + "attention.attention."
+            def merged(w, target):
+                d = self._lora_delta(sd, i, target)
+                return w if d is None else w.float() + d.to(w.device)
+
             L = {
                 "n1w": f32(sd[p + "norm1.weight"]), "n1b": f32(sd[p + "norm1.bias"]),
-                "wqkv": b16(torch.cat([sd[a + "query.weight"], sd[a + "key.weight"], sd[a + "value.weight"]], 0)),
+                "wqkv": b16(torch.cat([merged(sd[a + "query.weight"], "query"), merged(sd[a + "key.weight"], "key"),
+                                       merged(sd[a + "value.weight"], "value")], 0)),
                 "bqkv": f32(torch.cat([sd[a + "query.bias"], sd[a + "key.bias"], sd[a + "value.bias"]], 0)),
-                "wo": b16(sd[p + "attention.output.dense.weight"]), "bo": f32(sd[p + "attention.output.dense.bias"]),
+                "wo": b16(merged(sd[p + "attention.output.dense.weight"], "attention_output")),
+                "bo": f32(sd[p + "attention.output.dense.bias"]),
                 "ls1": f32(sd[p + "layer_scale1.lambda1"]),
                 "n2w": f32(sd[p + "norm2.weight"]), "n2b": f32(sd[p + "norm2.bias"]),
                 "w1": b16(sd[p + "mlp.fc1.weight"]), "b1": f32(sd[p + "mlp.fc1.bias"]),

@@ -131,10 +131,17 @@ class _CuriosityInit(nn.Module):  # CuriosityModule.__init__, src/model.py:524-5
 class _ModelInit(nn.Module):
     """Construction order of CognitiveAimModel.__init__ (src/model.py:798-958) under the effective config."""
 
-    def __init__(self, num_cameras=71, curiosity_guided=False):
+    def __init__(self, num_cameras=71, curiosity_guided=False, use_lora=False, lora_rank=16):
         super().__init__()
         from transformers import Dinov2Config, Dinov2Model  # the reference's own backbone dependency
         self.backbone = Dinov2Model(Dinov2Config(image_size=518, patch_size=14))  # :814 (offline: random init)
+        if use_lora:  # :822-831, LoRALayer.__init__ :15-24 (built and saved, never applied: quirk 4)
+            self.lora_layers = nn.ModuleList()
+            for _ in range(12):
+                lo = nn.Module()
+                lo.lora_A = nn.Parameter(torch.randn(lora_rank, 768) * 0.01)
+                lo.lora_B = nn.Parameter(torch.zeros(768, lora_rank))
+                self.lora_layers.append(lo)
         self.ambient_stream = nn.Module()
         self.ambient_stream.mlp = nn.Sequential(nn.Linear(768, 256), nn.ReLU(), nn.Dropout(0.1), nn.Linear(256, 128),
                                                 nn.ReLU(), nn.Linear(128, 64))  # :37-44
@@ -159,12 +166,14 @@ class _ModelInit(nn.Module):
         self.global_aligner = _AlignerInit(768, 768 * 3)  # :958
 
 
-def build_state_dict(seed: int = 0, num_cameras: int = 71, curiosity_guided: bool = False) -> SD:
+def build_state_dict(seed: int = 0, num_cameras: int = 71, curiosity_guided: bool = False,
+                     use_lora: bool = False) -> SD:
     """`torch.manual_seed(seed); create_model(cfg, {'num_cameras': 71}).state_dict()` of the reference
     (SURVEY.md §8c seed protocol), without the reference.  curiosity_guided=True is what a config with the top-level
-    key `curiosity_guided_attention: {enabled: true}` builds (src/model.py:854): 16 more tensors."""
+    key `curiosity_guided_attention: {enabled: true}` builds (src/model.py:854): 16 more tensors; use_lora=True is
+    top-level `use_lora: true` (:822): 24 more tensors that no forward path reads."""
     torch.manual_seed(seed)
-    m = _ModelInit(num_cameras, curiosity_guided).eval()
+    m = _ModelInit(num_cameras, curiosity_guided, use_lora).eval()
     return {k: v.detach().clone() for k, v in m.state_dict().items()}
 
 

@@ -7,6 +7,7 @@ network access at reference src/model.py:814 (`Dinov2Model.from_pretrained`) -> 
 
     python oracle/make_golden.py                    # writes tests/golden/*.npz / *.json
     python oracle/make_golden.py --only-curiosity   # only curiosity.npz / curiosity_guided.npz (sections 6-7)
+    python oracle/make_golden.py --only-lora        # only lora.npz / state_dict_seed0_lora.json (section 8)
 """
 from __future__ import annotations
 
@@ -134,12 +135,35 @@ def curiosity_sections(ref):
     print("curiosity-guided: state tensors", len(sd))
 
 
+def lora_section(ref):
+    """8. top-level `use_lora: true` (src/model.py:822-831): 24 LoRA tensors in the state_dict that no forward reads —
+    recorded with lora_B made non-zero, so that "the reference ignores its adapters" is a pinned fact."""
+    model = make_model(ref, os.path.join(REF, "configs", "experiment_B.yaml"), {"use_lora": True})
+    assert model.use_lora
+    sd = model.state_dict()
+    json.dump({"seed": WEIGHT_SEED, "names": list(sd.keys()), "shapes": {k: list(v.shape) for k, v in sd.items()},
+               "digest": orc.state_dict_digest(sd)}, open(os.path.join(OUT, "state_dict_seed0_lora.json"), "w"))
+    g = torch.Generator().manual_seed(77)
+    with torch.no_grad():
+        for lo in model.lora_layers:
+            lo.lora_B.copy_(torch.randn(lo.lora_B.shape, generator=g) * 0.05)
+    x, ex = orc.synthetic_images(2, 224), orc.synthetic_exif(2)
+    torch.manual_seed(CALL_SEED)
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        d, c, h = model.forward_with_guidance(x, ex, "center", return_attention=True)
+    np.savez_compressed(os.path.join(OUT, "lora.npz"), depth=d.numpy(), conf=c.numpy(), heat=h.numpy())
+    print("lora: state tensors", len(sd), "depth", d.ravel())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
     torch.set_num_threads(os.cpu_count())
     if "--only-curiosity" in sys.argv:
         curiosity_sections(ref)
+        return
+    if "--only-lora" in sys.argv:
+        lora_section(ref)
         return
 
     # 1. effective config of every shipped YAML (quirk 1) ------------------------------------------------
@@ -215,6 +239,7 @@ def main():
         out[f"S{S}_B{B}_token_norms"] = t.norm(dim=-1).numpy()
     np.savez_compressed(os.path.join(OUT, "backbone.npz"), **out)
     curiosity_sections(ref)
+    lora_section(ref)
     print("golden vectors written to", OUT)
 
 

@@ -105,6 +105,21 @@ def test_curiosity_guided_state_dict_is_reference_compatible():
         assert list(v.shape) == gold["shapes"][k], k
 
 
+def test_lora_state_dict_is_reference_compatible():
+    """Top-level `use_lora: true` (src/model.py:822-831): `lora_layers.{i}.lora_A / lora_B` right after the backbone."""
+    gold = json.load(open(os.path.join(GOLD, "state_dict_seed0_lora.json")))
+    m = create_model(dict(SHIPPED_LIKE, use_lora=True), {"num_cameras": 71})
+    sd = m.state_dict()
+    assert m.use_lora and list(sd.keys()) == gold["names"] and len(sd) == 343
+    for k, v in sd.items():
+        assert list(v.shape) == gold["shapes"][k], k
+    assert float(sd["lora_layers.3.lora_B"].abs().sum()) == 0.0
+    with pytest.raises(ValueError):
+        create_model(dict(SHIPPED_LIKE, lora_merge_target="query"), {"num_cameras": 71})       # needs use_lora
+    with pytest.raises(ValueError):
+        create_model(dict(SHIPPED_LIKE, use_lora=True, lora_merge_target="mlp"), {"num_cameras": 71})
+
+
 def test_tables_match_oracle_definitions():
     from oracle import cogaim_oracle as orc
     for g in (16, 37, 74):

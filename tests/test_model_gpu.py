@@ -155,3 +155,49 @@ def test_errors_are_raised_not_swallowed(model):
            "camera_idx": torch.tensor([99])}
     with pytest.raises(ValueError):
         model.forward_with_guidance(torch.zeros(1, 3, 224, 224).cuda(), bad, "center")
+
+
+def _lora_sd(scale=0.05):
+    sd = orc.build_state_dict(0, use_lora=True)
+    g = torch.Generator().manual_seed(77)
+    for i in range(12):
+        sd[f"lora_layers.{i}.lora_B"] = torch.randn(768, 16, generator=g) * scale
+    return sd
+
+
+def test_lora_adapters_are_ignored_like_the_reference(cuda_device):
+    """`use_lora: true` with NON-zero lora_B: the reference never applies its adapters (src/model.py:30, 824-831), so the
+    outputs must equal the fixture the unmodified reference produced from these very weights (tests/golden/lora.npz)."""
+    import os
+    from cognitive_aim_depth_estimation_b200.model import create_model
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "lora.npz"))
+    m = create_model(dict(CFG, use_lora=True), {"num_cameras": 71}, device=cuda_device)
+    m.load_state_dict(_lora_sd())
+    torch.manual_seed(11)
+    d, c, h = m.forward_with_guidance(orc.synthetic_images(2, 224).cuda(), _cuda_exif(orc.synthetic_exif(2), "cuda"),
+                                      "center", return_attention=True)
+    assert (np.abs(d.cpu().numpy() - gold["depth"]) / np.abs(gold["depth"])).max() <= DEPTH_ABS_REL
+    assert np.abs(h.cpu().numpy() - gold["heat"]).max() <= HEAT_MAX_ABS
+    assert (h.cpu().numpy().argmax(-1) == gold["heat"].argmax(-1)).all()
+
+
+@pytest.mark.parametrize("target", ["query", "attention_output"])
+def test_lora_merge_target_applies_the_adapters(cuda_device, target):
+    """The opt-in (non-reference) `lora_merge_target`: y = W x + (alpha / rank) B A x on the chosen 768 -> 768 projection
+    of every encoder layer, checked against a plain fp32 restatement (the oracle backbone with W + (16/16) B A)."""
+    from cognitive_aim_depth_estimation_b200.model import create_model
+    sd = _lora_sd(0.5)  # B A of the same size as the weight it adapts
+    name = {"query": "attention.attention.query.weight", "attention_output": "attention.output.dense.weight"}[target]
+    merged = dict(sd)
+    for i in range(12):
+        k = f"backbone.encoder.layer.{i}.{name}"
+        merged[k] = sd[k] + sd[f"lora_layers.{i}.lora_B"] @ sd[f"lora_layers.{i}.lora_A"]
+    x = orc.synthetic_images(2, 224)
+    want, plain = orc.dinov2_tokens(merged, x), orc.dinov2_tokens(sd, x)
+    m = create_model(dict(CFG, use_lora=True, lora_merge_target=target), {"num_cameras": 71}, device=cuda_device)
+    m.load_state_dict(sd)
+    tok = m.backbone_tokens(x.cuda()).cpu()
+    rel = ((tok - want).norm() / want.norm()).item()
+    moved = ((plain - want).norm() / want.norm()).item()
+    assert rel < TOKEN_REL_FRO, rel
+    assert moved > 3 * rel, (moved, rel)  # the adapters really changed the tokens

@@ -220,3 +220,20 @@ def test_curiosity_guided_state_dict_and_forward():
         np.testing.assert_allclose(o["depth"].numpy(), gold[f"guided_{ins}_depth"], rtol=2e-5)
         np.testing.assert_allclose(o["heatmap"].numpy(), gold[f"guided_{ins}_heat"], rtol=2e-3, atol=1e-9)
         assert (o["heatmap"].argmax(-1).numpy() == gold[f"guided_{ins}_heat"].argmax(-1)).all()
+
+
+def test_lora_is_built_saved_and_ignored_by_the_reference():
+    """Top-level `use_lora: true` (src/model.py:822-831): 24 more tensors, bit-identical init, and a forward that never
+    reads them — the fixture was recorded with non-zero lora_B; the oracle, which has no LoRA code at all, reproduces it."""
+    gold_sd = json.load(open(os.path.join(GOLD, "state_dict_seed0_lora.json")))
+    sd = orc.build_state_dict(0, use_lora=True)
+    assert list(sd.keys()) == gold_sd["names"] and len(sd) == 343
+    for k, v in sd.items():
+        s, a = gold_sd["digest"][k]
+        assert float(v.double().sum()) == s and float(v.double().abs().sum()) == a, k
+    assert float(sd["lora_layers.0.lora_B"].abs().sum()) == 0.0
+    gold = np.load(os.path.join(GOLD, "lora.npz"))
+    torch.manual_seed(11)
+    out = orc.forward_with_guidance(sd, orc.synthetic_images(2, 224), orc.synthetic_exif(2), "center", update_history=False)
+    np.testing.assert_allclose(out["depth"].numpy(), gold["depth"], rtol=2e-5)
+    np.testing.assert_allclose(out["heatmap"].numpy(), gold["heat"], rtol=2e-3, atol=1e-9)
