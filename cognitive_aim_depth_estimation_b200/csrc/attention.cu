@@ -61,6 +61,44 @@ constexpr int kItemQ = 8;            // depth of the per-CTA item queue (power o
 #define CA_ATTN_POLY_MASK 0x5555
 #endif
 constexpr unsigned kPolyMask = CA_ATTN_POLY_MASK;
+// Waits of the control warps (TMA producer on scheduler 0, MMA issuer on scheduler 1, which they share with softmax
+// warps 4 and 5 of both resident CTAs): parked by the hardware instead of polled.
+// CA_ATTN_ABLATE (compile time, timing experiments only — results are wrong): 1 = exponentials do not wait for the
+// step's row maximum, 2 = no exponentials, 4 = no K / V traffic after the first ring fill.  What they showed
+// (B=32, T=1370): 0.263 ms -> 0.251 (1) / 0.234 (2) / 0.228 (3) / 0.262 (4) / 0.221 (7): neither the MUFU nor the L2
+// stream bounds the kernel; the per-step protocol does (profiles/README.md, "attention timeline").
+#ifndef CA_ATTN_ABLATE
+#define CA_ATTN_ABLATE 0
+#endif
+// CA_ATTN_PREFETCH=1: pull the next step's S row into registers before this step's store wait / hand-over.  Measured
+// same-box: SLOWER (0.265 -> 0.303 ms; 168 registers and a few spills instead of 152), so it is off.
+#ifndef CA_ATTN_PREFETCH
+#define CA_ATTN_PREFETCH 0
+#endif
+// CA_ATTN_TRACE=1 (compile time) + CA_ATTN_DEBUG (run time): CTA 0 records clock64() at the phase boundaries of its first
+// kTraceSteps steps (softmax warp 2 lane 0: 4 slots; MMA warp: 4 slots); the launcher prints the timeline.
+#ifndef CA_ATTN_TRACE
+#define CA_ATTN_TRACE 0
+#endif
+constexpr int kTraceSteps = 96;
+constexpr int kTraceBase = 2 * 1024;  // offset into the debug buffer (roles: 0 softmax, 1 MMA, 2 boundary detail)
+#if CA_ATTN_TRACE
+#define TRACE(role, step, slot)                                                                              \
+  do {                                                                                                       \
+    if (p.dbg && blockIdx.x == 0 && lane == 0 && (step) < kTraceSteps)                                       \
+      p.dbg[kTraceBase + ((role) * kTraceSteps + (step)) * 4 + (slot)] = clock64();                          \
+  } while (0)
+#else
+#define TRACE(role, step, slot) do {} while (0)
+#endif
+#ifndef CA_ATTN_PARKED_WAITS
+#define CA_ATTN_PARKED_WAITS 1
+#endif
+#if CA_ATTN_PARKED_WAITS
+#define CTRL_WAIT(bar, parity) mbar_wait_parked(bar, parity)
+#else
+#define CTRL_WAIT(bar, parity) mbar_wait(bar, parity)
+#endif
 constexpr float kLazyLimit = 8.0f;  // the accumulator reference moves only when a row max grew by > 2^8
 
 struct AttnArgs {
@@ -185,9 +223,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
           k_col = (p.H + bh - k_b * p.H) * kHeadDim;
         }
         const int s = kg % kRing;
-        mbar_wait(&k_empty[s], ((kg / kRing) & 1) ^ 1u);
+        CTRL_WAIT(&k_empty[s], ((kg / kRing) & 1) ^ 1u);
+#if CA_ATTN_ABLATE & 4   // timing experiment: no K / V traffic after the first ring fill
+        if (kg >= kRing) { mbar_arrive(&k_full[s]); } else
+#endif
+        {
         mbar_arrive_expect_tx(&k_full[s], kSubBytes);
         tma_load_3d(smem + kSmemK + s * kSubBytes, &tmap_kv, &k_full[s], k_col, k_step * kSubK, k_b);
+        }
         ++kg;
         if (++k_step == n_sub) {
           k_step = 0;
@@ -204,9 +247,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
           v_col = (2 * p.H + bh - v_b * p.H) * kHeadDim;
         }
         const int s = vg % kRing;
-        mbar_wait(&v_empty[s], ((vg / kRing) & 1) ^ 1u);
+        CTRL_WAIT(&v_empty[s], ((vg / kRing) & 1) ^ 1u);
+#if CA_ATTN_ABLATE & 4
+        if (vg >= kRing) { mbar_arrive(&v_full[s]); } else
+#endif
+        {
         mbar_arrive_expect_tx(&v_full[s], kSubBytes);
         tma_load_3d(smem + kSmemV + s * kSubBytes, &tmap_kv, &v_full[s], v_col, v_step * kSubK, v_b);
+        }
         ++vg;
         if (++v_step == n_sub) {
           v_step = 0;
@@ -229,10 +277,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
       if (!s_more) return;
       if (s_step == 0) {  // first S of an item: the item must exist and its Q tile must be in TMEM
         if (read_item(s_item) < 0) { s_more = false; return; }
-        mbar_wait(&q_ready[s_item & 1], (s_item >> 1) & 1);
+        CTRL_WAIT(&q_ready[s_item & 1], (s_item >> 1) & 1);
       }
       const int s = sg % kRing;
-      mbar_wait(&k_full[s], (sg / kRing) & 1);
+      CTRL_WAIT(&k_full[s], (sg / kRing) & 1);
       tc_fence_after();
       if (elect_one_sync()) {
         const uint64_t kd = kd0 + s * kSubStep;
@@ -254,8 +302,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
       for (int i = 0; i < n_sub; ++i, ++g) {
         const int bb = g & 1;
         const int s = g % kRing;
-        mbar_wait(&v_full[s], (g / kRing) & 1);
-        mbar_wait(&p_full[bb], (g >> 1) & 1);  // on step 0 of an item this also hands O over (previous item read out)
+        TRACE(1, g, 0);
+        CTRL_WAIT(&v_full[s], (g / kRing) & 1);
+        TRACE(1, g, 1);
+        CTRL_WAIT(&p_full[bb], (g >> 1) & 1);  // on step 0 of an item this also hands O over (previous item read out)
+        TRACE(1, g, 2);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint64_t vd = vd0 + s * kSubStep;
@@ -271,6 +322,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
         }
         __syncwarp();
         issue_s();  // S of step g+2: overwrites S_g / P_g, ordered behind PV_g by the in-order tensor pipe
+        TRACE(1, g, 3);
       }
     }
   } else {
@@ -279,6 +331,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const uint32_t t_o = t_lane + kTmemO;
     const float scale = p.scale_log2;
+    int g = 0;  // global 64-key step of this CTA
     // Q row of an item: global -> registers (rows past the end of the image are zero)
     auto q_load = [&](int it, uint32_t (&qv)[32]) {
       const int bh = it / p.n_qt;
@@ -303,6 +356,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
       const int b = bh / p.H;
       const int h = bh - b * p.H;
       mbar_wait(o_full, k & 1);
+      if (warp == 2) TRACE(2, g, 0);
       tc_fence_after();
       const float inv = 1.0f / l;
       __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * p.T + q) * p.ldo + h * kHeadDim;
@@ -340,9 +394,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
       if (lane == 0) mbar_arrive(&q_ready[0]);
     }
     float l_prev = 1.f;
-    int g = 0;
     int k = 0;
     float m_acc = -INFINITY, l_run = 0.f;  // reference (log2 domain) O and l_run are expressed in; running row sum
+    uint32_t v[64];        // the S row of the current step (fp32 bits); may already hold the NEXT step's row (have_v)
+    bool have_v = false;
     // One 64-key step.  kBoundary = step 0 of an item, which also carries the previous item's epilogue and the next
     // item's Q tile; it is a separate instantiation so that the steady-state step stays lean.
     auto step = [&](auto boundary_tag, const int i) {
@@ -355,16 +410,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
         it_next = read_item(k + 1);
         if (it_next >= 0) q_load(it_next, qv);  // in flight under this step's exponentials
       }
-      uint32_t v[64];
-      mbar_wait(&s_full[bb], (g >> 1) & 1);
-      tc_fence_after();
-      {
-        uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-        uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+      uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+      uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+      if (warp == 2) TRACE(0, g, 0);
+      if (!have_v) {  // not prefetched at the end of the previous step
+        mbar_wait(&s_full[bb], (g >> 1) & 1);
+        tc_fence_after();
         tmem_ld32(t_s, v0);
         tmem_ld32(t_s + 32, v1);
-        tmem_ld_wait();
       }
+      if (warp == 2) TRACE(0, g, 1);
+      tmem_ld_wait();
       if (valid < kSubK) {
 #pragma unroll
         for (int c = 0; c < kSubK; ++c)
@@ -382,7 +438,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
           m3 = fmaxf(m3, fmaxf(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7])));
         }
       }
+#if CA_ATTN_ABLATE & 1   // timing experiment: no dependency of the exponentials on this step's maximum
+      const float tile_max = boundary ? fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale : m_acc;
+#else
       const float tile_max = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale;  // scale > 0
+#endif
       // ---- lazy reference update (warp-uniform decision; always taken on the first step of an item) ----
       if (__any_sync(0xffffffffu, tile_max > m_acc + kLazyLimit)) {
         const float m_new = fmaxf(m_acc, tile_max);
@@ -413,6 +473,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
 #pragma unroll
         for (int kk = 0; kk < 8; kk += 2) {
           ffma2(e[kk], e[kk + 1], __uint_as_float(v[8 * t + kk]), __uint_as_float(v[8 * t + kk + 1]), scale, neg_m);
+#if CA_ATTN_ABLATE & 2   // timing experiment: no exponentials at all
+          if (!boundary) continue;
+#endif
           if (kk >= 8 - 2 * static_cast<int>((kPolyMask >> (2 * t)) & 3u)) {  // compile-time split MUFU / polynomial
             exp2_poly2(e[kk], e[kk + 1]);
           } else {
@@ -429,23 +492,38 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
         pk[4 * t + 2] = pack_bf16x2(e[4], e[5]);
         pk[4 * t + 3] = pack_bf16x2(e[6], e[7]);
       }
+      if (warp == 2) TRACE(0, g, 2);
       tmem_st32(t_s, pk);
       l_run += (s0 + s1) + (s2 + s3);
       if constexpr (boundary) {
         // the previous item's last P V has long finished: read its O out before this step's P V may overwrite it
         if (k > 0) epilogue(k - 1, it_prev, l_prev);
+        if (warp == 2) TRACE(2, g, 1);
         if (it_next >= 0) {  // Q of the next item (its buffer was last read by item k-1, which is complete)
           tmem_st32(t_lane + kTmemQ + ((k + 1) & 1) * 32, qv);
           tmem_st_wait();
+          if (warp == 2) TRACE(2, g, 2);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&q_ready[(k + 1) & 1]);
         }
       }
+      // S of the next step of this item (issued two steps ago, normally long complete) starts its way into registers now,
+      // under the store wait / fence / hand-over of this step, instead of after them.
+      have_v = false;
+#if CA_ATTN_PREFETCH
+      if (i + 1 < n_sub && __all_sync(0xffffffffu, mbar_try_wait(&s_full[bb ^ 1], ((g + 1) >> 1) & 1))) {
+        tc_fence_after();
+        tmem_ld32(t_lane + kTmemS + (bb ^ 1) * kSubK, v0);
+        tmem_ld32(t_lane + kTmemS + (bb ^ 1) * kSubK + 32, v1);
+        have_v = true;
+      }
+#endif
       tmem_st_wait();     // P (and a rescaled O) are in TMEM
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[bb]);
+      if (warp == 2) TRACE(0, g, 3);
       ++g;
     };
     while (it_cur >= 0) {
@@ -528,7 +606,10 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
   static long long* d_dbg = nullptr;
   a.dbg = nullptr;
   if (want_dbg) {
-    if (!d_dbg) CA_CUDA(cudaMalloc(&d_dbg, 2 * 1024 * sizeof(long long)));
+    if (!d_dbg) {
+      CA_CUDA(cudaMalloc(&d_dbg, (kTraceBase + 3 * kTraceSteps * 4) * sizeof(long long)));
+      CA_CUDA(cudaMemset(d_dbg, 0, (kTraceBase + 3 * kTraceSteps * 4) * sizeof(long long)));
+    }
     a.dbg = d_dbg;
   }
   attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tm_kv, a);
@@ -547,6 +628,24 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
         sum += h[2 * i];
       }
       fprintf(stderr, "[attn dbg] grid %d cycles/CTA min %lld mean %.0f max %lld\n", grid, mn, sum / grid, mx);
+#if CA_ATTN_TRACE
+      {
+        static long long tr[3 * kTraceSteps * 4];
+        CA_CUDA(cudaMemcpy(tr, d_dbg + kTraceBase, sizeof(tr), cudaMemcpyDeviceToHost));
+        const long long t0 = tr[0];
+        fprintf(stderr, "[attn trace] CTA 0, n_sub %d; per step: softmax {wait_s_begin, s_ready, exps_done, p_arrived} | "
+                        "mma {begin, v_ready, p_ready, issued}  (cycles since the first event)\n", a.n_sub);
+        for (int g2 = 0; g2 < kTraceSteps; ++g2) {
+          const long long* sm = tr + g2 * 4;
+          const long long* mm = tr + (kTraceSteps + g2) * 4;
+          const long long* bd = tr + (2 * kTraceSteps + g2) * 4;
+          fprintf(stderr, "  step %2d  sm %7lld %7lld %7lld %7lld | mma %7lld %7lld %7lld %7lld", g2, sm[0] - t0,
+                  sm[1] - t0, sm[2] - t0, sm[3] - t0, mm[0] - t0, mm[1] - t0, mm[2] - t0, mm[3] - t0);
+          if (bd[0]) fprintf(stderr, " | boundary {o_full, O stored, Q in TMEM} %7lld %7lld %7lld", bd[0] - t0, bd[1] - t0, bd[2] - t0);
+          fprintf(stderr, "\n");
+        }
+      }
+#endif
       for (int i = 0; i < grid; i += 16) fprintf(stderr, "  cta %3d sm %3lld cycles %lld\n", i, h[2 * i + 1], h[2 * i]);
     }
   }

@@ -143,6 +143,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware may keep the thread parked (no issue slots spent) for up to `ns`
+// before reporting failure, and wakes it as soon as the phase completes.  For the control warps (TMA producer, MMA
+// issuer) that share a scheduler with compute warps, a plain try_wait loop returns after a short default window and
+// spends ~13 instructions per retry on that scheduler.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as
 // a hung GPU.  ~4e9 cycles is >2 s at any B200 clock, far beyond any legitimate wait here.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -151,6 +166,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ffu) == 0 && (clock64() - t0) > 4000000000LL) {
+      printf("[cogaim] mbarrier wait timed out: block (%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+// The same bounded wait for control warps: parked by the hardware between retries (see mbar_try_wait_hint).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t ns = 20000u) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, ns)) {
+    if ((++spins & 0x3fu) == 0 && (clock64() - t0) > 4000000000LL) {
       printf("[cogaim] mbarrier wait timed out: block (%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
       __trap();

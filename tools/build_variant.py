@@ -1,5 +1,5 @@
 """Build the C-ABI library of another git revision (or the working tree) next to the current one, for same-box A/B
-timing:  python tools/build_variant.py <rev|WORK> <name>  ->  build/variants/<name>/libcogaim_b200.so"""
+timing:  python tools/build_variant.py <rev|WORK> <name> [-DMACRO=v ...]  ->  build/variants/<name>/libcogaim_b200.so"""
 import concurrent.futures as cf
 import os
 import subprocess
@@ -24,7 +24,7 @@ for f in files:
     out.write_bytes(get(f))
 srcs = sorted((dst / "pkg" / "csrc").glob("*.cu"))
 flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", f"-I{dst / 'include'}"]
+         "--expt-relaxed-constexpr", f"-I{dst / 'include'}", *sys.argv[3:]]
 
 
 def cc(s):
