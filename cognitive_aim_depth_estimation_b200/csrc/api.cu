@@ -6,6 +6,7 @@
 #include "focal.cuh"
 #include "gemm.cuh"
 #include "heads.cuh"
+#include "jpeg.cuh"
 #include "visual.cuh"
 #include "resize.cuh"
 #include "rowops.cuh"
@@ -165,6 +166,14 @@ int ca_curiosity_modulation(const ca_curiosity_mod_weights* w, const float* rewa
 int ca_resize_u8(const uint8_t* src, int B, int H0, int W0, int out_h, int out_w, uint8_t* tmp, uint8_t* out,
                  void* stream) {
   return ca::resize_u8_launch(src, B, H0, W0, out_h, out_w, tmp, out, static_cast<cudaStream_t>(stream));
+}
+
+int ca_jpeg_info(const uint8_t* h_data, size_t len, int* width, int* height) {
+  return ca::jpeg_info(h_data, len, width, height, nullptr);
+}
+
+int ca_jpeg_decode(const uint8_t* h_data, size_t len, uint8_t* out_rgb, int width, int height, void* stream) {
+  return ca::jpeg_decode(h_data, len, out_rgb, width, height, static_cast<cudaStream_t>(stream));
 }
 
 int ca_focus_map(const float* heat, int B, int g, int out_h, int out_w, float* norm, float* out, void* stream) {

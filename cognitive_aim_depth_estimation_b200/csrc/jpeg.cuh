@@ -1,0 +1,13 @@
+// JPEG byte stream (host) -> uint8 RGB HWC (device) through nvJPEG (csrc/jpeg.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace ca {
+
+int jpeg_info(const uint8_t* h_data, size_t len, int* width, int* height, int* components);
+int jpeg_decode(const uint8_t* h_data, size_t len, uint8_t* out_rgb, int width, int height, cudaStream_t stream);
+
+}  // namespace ca

@@ -19,6 +19,7 @@ Differences that are deliberate:
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 from typing import Dict, Optional
@@ -597,6 +598,25 @@ class CognitiveAimModel(nn.Module):
         un-guided attention runs is clamped to [0.5, 1] (src/model.py:1107, :1141); the others are not."""
         pk = self._packed
         cm = self.curiosity_module
+        # Output-dead under the shipped configurations and latency-bound (one CTA per image through ten small dense
+        # layers): it runs on a side stream, forked here and joined by `_curiosity_join`, under the focal stream's GEMMs.
+        # The fork / join are stream dependencies, so they are captured into the CUDA graph as a parallel branch.
+        side = None
+        if not self.cfg.curiosity_guided and not ops.tracing_events():
+            side = getattr(self, "_side_stream", None)
+            if side is None or side.device != self._device():
+                side = self._side_stream = torch.cuda.Stream(device=self._device())
+            side.wait_stream(torch.cuda.current_stream())
+        self._curiosity_side = side
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            self._curiosity_launches(ws, B, T, roles, pk, cm)
+
+    def _curiosity_join(self):
+        side, self._curiosity_side = getattr(self, "_curiosity_side", None), None
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+
+    def _curiosity_launches(self, ws, B, T, roles, pk, cm):
         for j, role in enumerate(roles):
             ops.curiosity(pk["curiosity"], tokens=ws["tokens"], tokens_per_img=T, eps=ws["cur_eps"][j],
                           noise=ws["cur_noise"][j], reward_raw=ws["cur_raw"][j], reward=ws["cur_reward"][j],
@@ -660,6 +680,7 @@ class CognitiveAimModel(nn.Module):
             ops.heads(pk["heads"], tokens=ws["tokens"], tokens_per_img=T, depth=ws["depth"], conf=ws["conf"], B=B,
                       pool_partial=ws["pool"], pool_splits=_POOL_SPLITS, tmp_w=ws["tmpw"], tmp_b=ws["tmpb"],
                       pooled_out=ws["pooled"], exif=ws["exif_in"], camera_idx=ws["cam_in"])
+            self._curiosity_join()
 
         self._run(ws, ("guided", self._curiosity_key()), device_pass)
         # keep the temporaries referenced until the next call (their copies are enqueued, not finished)
@@ -738,6 +759,7 @@ class CognitiveAimModel(nn.Module):
             ops.heads(pk["heads"], tokens=ws["tokens"], tokens_per_img=T, depth=ws["depth"], conf=ws["conf"], B=B,
                       focal_feat=ws["focal_feat"], exif=ws["exif_in"] if has_exif else None,
                       camera_idx=ws["cam_in"] if has_exif else None, fused_out=ws["fused"])
+            self._curiosity_join()
 
         self._run(ws, ("unguided", has_exif, tuple(roles), mask is not None, self._curiosity_key()), device_pass)
         self._keepalive = (exif, cam, images, mask)
@@ -828,6 +850,19 @@ class CognitiveAimModel(nn.Module):
         m = torch.tensor(mean, device=dev).view(1, 3, 1, 1)
         s = torch.tensor(std, device=dev).view(1, 3, 1, 1)
         return x.sub_(m).div_(s).contiguous()                          # Normalize
+
+    @torch.no_grad()
+    def preprocess_jpeg(self, jpeg_files, size: int, mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD):
+        """demo.py:312-319 for a list of JPEG files given as bytes: decode (nvJPEG) -> Resize((size, size)) (exact Pillow
+        arithmetic) -> ToTensor -> Normalize, all on the GPU.  Images may differ in size (each is resized on its own, as
+        `predict_batch` does, demo.py:406-432).  Returns float32 [B, 3, size, size]."""
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("preprocess_jpeg runs only on a CUDA sm_100 device; there is no CPU fallback")
+        if len(jpeg_files) == 0:
+            raise ValueError("empty list of JPEG files")
+        out = [self.preprocess(ops.jpeg_decode(f, dev).unsqueeze(0), size, mean, std) for f in jpeg_files]
+        return torch.cat(out, dim=0)
 
     @torch.no_grad()
     def tokens_from_uint8(self, images_hwc_u8: torch.Tensor, size: Optional[int] = None):

@@ -239,6 +239,24 @@ def resize_u8(src, out_h, out_w):
     return out
 
 
+def jpeg_decode(data: bytes, device=None):
+    """One JPEG file's bytes -> uint8 [H, W, 3] RGB CUDA tensor, decoded by nvJPEG on the current stream
+    (csrc/jpeg.cu; reference demo.py:312 `Image.open(path).convert('RGB')`)."""
+    import ctypes as C
+    if not isinstance(data, (bytes, bytearray, memoryview)):
+        raise ValueError("jpeg_decode expects the file's bytes")
+    data = bytes(data)
+    lib = _lib.load()
+    w, h = C.c_int(0), C.c_int(0)
+    check(lib.ca_jpeg_info(data, len(data), C.byref(w), C.byref(h)), "ca_jpeg_info")
+    out = torch.empty(h.value, w.value, 3, device=device or "cuda", dtype=torch.uint8)
+    e0 = _begin()
+    with torch.cuda.device(out.device):
+        check(lib.ca_jpeg_decode(data, len(data), ptr(out), w.value, h.value, stream_ptr()), "ca_jpeg_decode")
+    _end(e0, "jpeg", 1, float(out.numel()))
+    return out
+
+
 def focus_map(heat, g, out_h, out_w, norm, out):
     """norm [B, g*g], out [B, out_h, out_w] (or None): heat-map post-processing of demo.py:530-563 (csrc/visual.cu)."""
     _req(heat, torch.float32, "heat")

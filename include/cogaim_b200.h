@@ -204,6 +204,15 @@ int ca_curiosity_modulation(const ca_curiosity_mod_weights* w, const float* rewa
 int ca_resize_u8(const uint8_t* src, int B, int H0, int W0, int out_h, int out_w, uint8_t* tmp, uint8_t* out,
                  void* stream);
 
+/* ---- demo.py:312 `Image.open(path).convert('RGB')`: JPEG ingest through nvJPEG (CUDA toolkit; loaded lazily) ---------
+ * h_data / len: one JPEG file's bytes in HOST memory.  ca_jpeg_info fills the decoded size; ca_jpeg_decode writes
+ * height*width*3 bytes of interleaved RGB to the DEVICE buffer out_rgb on `stream` (grayscale streams are expanded to
+ * RGB like PIL's convert).  Without nvJPEG both return CA_STATUS_UNSUPPORTED: there is no CPU decode fallback.
+ * nvJPEG and libjpeg-turbo (inside Pillow) are different decoders: with the interpolating chroma up-sampler requested
+ * here the results agree to <= 5 LSB (mean ~0.6), not bit for bit (tests/test_jpeg_gpu.py states the tolerance). */
+int ca_jpeg_info(const uint8_t* h_data, size_t len, int* width, int* height);
+int ca_jpeg_decode(const uint8_t* h_data, size_t len, uint8_t* out_rgb, int width, int height, void* stream);
+
 /* ---- visualisation post-processing (the consumer right after the hot path; replaces demo.py:530-563) ------------
  * norm[b, :]  = min-max( where(a > percentile70(a), a, 0.3 a) ),  a = heat[b, :]^3            (numpy float32 semantics)
  * out[b,y,x]  = scipy.ndimage.zoom(norm[b].reshape(g, g), (out_h / g, out_w / g), order=1)    (skipped when out is null)

@@ -1,0 +1,88 @@
+"""JPEG ingest: nvJPEG decode on the GPU against Pillow's libjpeg-turbo decode of the same bytes
+(reference demo.py:312 `Image.open(path).convert('RGB')`), and the decode -> resize -> normalise chain against demo.py's
+PIL + torchvision chain.  Two different decoders: the IDCT and the chroma up-sampling are allowed to differ by a few
+LSB, which is the tolerance stated here; everything after the decode is bit-exact on equal pixels (test_rowops_gpu.py)."""
+import io
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import cogaim_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+# |nvJPEG - libjpeg-turbo| per 8-bit channel value; tools/jpeg_probe.py measured max 4-5, mean 0.49-0.73 on these very
+# images (IDCT / colour-conversion rounding; chroma up-sampled with interpolation on both sides).  With nvJPEG's default
+# chroma replication the maximum at hard colour edges would be ~80: csrc/jpeg.cu asks for the interpolating up-sampler.
+MAX_ABS_444, MEAN_ABS_444 = 6, 0.9
+MAX_ABS_SUB, MEAN_ABS_SUB = 6, 0.9
+
+
+def _synthetic(h, w, seed):
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.stack([127 + 100 * np.sin(x / 37.0 + seed) * np.cos(y / 53.0), 127 + 90 * np.cos((x + y) / 71.0),
+                    255 * (x / w) * (y / h)], -1)
+    img[h // 4: h // 2, w // 3: w // 2] = (200, 30, 60)  # a hard-edged block
+    img += rng.normal(0, 6, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def _jpeg(arr, quality, subsampling):
+    buf = io.BytesIO()
+    Image.fromarray(arr).save(buf, format="JPEG", quality=quality, subsampling=subsampling)
+    return buf.getvalue()
+
+
+@pytest.mark.parametrize("h,w", [(480, 640), (517, 389), (64, 48)])
+@pytest.mark.parametrize("subsampling,quality", [(0, 95), (2, 95), (2, 75), (1, 90)])
+def test_decode_matches_pillow(cuda_device, h, w, subsampling, quality):
+    from cognitive_aim_depth_estimation_b200 import ops
+    data = _jpeg(_synthetic(h, w, h + subsampling), quality, subsampling)
+    ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB")).astype(np.int32)
+    got = ops.jpeg_decode(data).cpu().numpy().astype(np.int32)
+    assert got.shape == ref.shape == (h, w, 3)
+    d = np.abs(got - ref)
+    mx, mean = (MAX_ABS_444, MEAN_ABS_444) if subsampling == 0 else (MAX_ABS_SUB, MEAN_ABS_SUB)
+    assert d.max() <= mx and d.mean() <= mean, (d.max(), d.mean())
+
+
+def test_grayscale_and_errors(cuda_device):
+    from cognitive_aim_depth_estimation_b200 import ops
+    from cognitive_aim_depth_estimation_b200._lib import CogAimError
+    buf = io.BytesIO()
+    Image.fromarray(_synthetic(100, 120, 1)[..., 0]).save(buf, format="JPEG", quality=90)
+    data = buf.getvalue()
+    ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB")).astype(np.int32)
+    got = ops.jpeg_decode(data).cpu().numpy().astype(np.int32)
+    assert got.shape == (100, 120, 3) and np.abs(got - ref).max() <= MAX_ABS_444
+    with pytest.raises(CogAimError):
+        ops.jpeg_decode(b"this is not a jpeg stream at all")
+    with pytest.raises(ValueError):
+        ops.jpeg_decode("a/path.jpg")
+
+
+def test_jpeg_to_tokens_matches_demo_chain(cuda_device):
+    """demo.py:312-319 end to end for two files of different sizes: nvJPEG -> exact-Pillow resize -> normalise on the GPU
+    vs PIL decode -> torchvision Resize / ToTensor / Normalize on the CPU; then the backbone on both."""
+    from torchvision import transforms
+    from cognitive_aim_depth_estimation_b200.model import create_model
+    cfg = {"model": {"cognitive_modules": ["ambient_stream", "iterative_focal_stream", "exif_prior_database"]}}
+    m = create_model(cfg, {"num_cameras": 71}, device=cuda_device)
+    m.load_state_dict(orc.build_state_dict(0))
+    files = [_jpeg(_synthetic(480, 640, 3), 95, 0), _jpeg(_synthetic(300, 400, 4), 90, 2)]
+    tf = transforms.Compose([transforms.Resize((224, 224)), transforms.ToTensor(),
+                             transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    want = torch.stack([tf(Image.open(io.BytesIO(f)).convert("RGB")) for f in files])
+    got = m.preprocess_jpeg(files, 224)
+    assert got.shape == (2, 3, 224, 224)
+    # one LSB of a pixel is 1 / (255 * 0.225) = 0.0174 in the normalised domain; the resize is bit-exact on equal pixels,
+    # so what is left is the decoders' difference (mean ~0.5 LSB, measured 0.0090) carried through the resample
+    d = (got.cpu() - want).abs()
+    assert d.max().item() <= 4 * 0.0175 and d.mean().item() <= 0.9 * 0.0175, (d.max().item(), d.mean().item())
+    t_got, t_want = m.backbone_tokens(got).clone(), m.backbone_tokens(want.cuda()).clone()
+    # a ~1 % input perturbation (0.009 on unit-variance pixels) through the random-init ViT stays a ~1 % token perturbation
+    rel = ((t_got - t_want).norm() / t_want.norm()).item()
+    assert rel < 3e-2, rel
