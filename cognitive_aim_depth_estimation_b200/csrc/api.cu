@@ -103,6 +103,10 @@ int ca_focal_input(const float* tokens, const float* pe, const float* rowscale, 
                                 static_cast<cudaStream_t>(stream));
 }
 
+int ca_fetch_pinned_f32(float* dst, const float* h_src_pinned, size_t n, void* stream) {
+  return ca::fetch_pinned_launch(dst, h_src_pinned, n, static_cast<cudaStream_t>(stream));
+}
+
 int ca_rowstats_merge(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, float* wtab,
                       int rows, int P, void* stream) {
   return ca::rowstats_merge_launch(pm, ps, weight, rmax, rinv, wtab, rows, P, static_cast<cudaStream_t>(stream));

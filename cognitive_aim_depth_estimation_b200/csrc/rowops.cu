@@ -192,6 +192,27 @@ int preprocess_u8_launch(const uint8_t* images, __nv_bfloat16* patches, int B, i
   return 0;
 }
 
+// dst[i] = src[i], src in PINNED HOST memory read by the SMs over PCIe (UVA).  For the few hundred KB of per-call inputs
+// (per-call projection, curiosity draws): a cudaMemcpyAsync would queue on the H2D copy engine behind whatever bulk
+// upload the application has in flight there (the next image batch, ~2 ms) and stall the compute stream for that long.
+__global__ void fetch_pinned_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[i];
+}
+
+int fetch_pinned_launch(float* dst, const float* src_pinned_host, size_t n, cudaStream_t stream) {
+  CA_REQUIRE(dst && src_pinned_host, "fetch_pinned: null pointer");
+  if (n == 0) return 0;
+  cudaPointerAttributes attr;
+  CA_CUDA(cudaPointerGetAttributes(&attr, src_pinned_host));
+  CA_REQUIRE(attr.type == cudaMemoryTypeHost, "fetch_pinned: the source must be page-locked (pinned) host memory");
+  const int grid = static_cast<int>((n + 255) / 256 < 64 ? (n + 255) / 256 : 64);
+  fetch_pinned_kernel<<<grid, 256, 0, stream>>>(dst, static_cast<const float*>(attr.devicePointer), n);
+  CA_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int cls_rows_launch(float* x, const float* cls, const float* pos, int B, int T, int D, cudaStream_t stream) {
   CA_REQUIRE(x && cls && pos, "cls_rows: null pointer");
   cls_rows_kernel<<<(B * D + 255) / 256, 256, 0, stream>>>(x, cls, pos, B, T, D);

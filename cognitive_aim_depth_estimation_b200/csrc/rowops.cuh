@@ -12,6 +12,7 @@ constexpr int kPatchRowStride = 592;  // 3*14*14 = 588 padded to a 16-byte multi
 int patchify_f32_launch(const float* images, __nv_bfloat16* patches, int B, int S, cudaStream_t stream);
 int preprocess_u8_launch(const uint8_t* images, __nv_bfloat16* patches, int B, int S, const float* mean3,
                          const float* std3, cudaStream_t stream);
+int fetch_pinned_launch(float* dst, const float* src_pinned_host, size_t n, cudaStream_t stream);
 int cls_rows_launch(float* x, const float* cls, const float* pos, int B, int T, int D, cudaStream_t stream);
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, int out_is_bf16, int rows, int D,
                      float eps, cudaStream_t stream);

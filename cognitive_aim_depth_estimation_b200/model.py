@@ -433,14 +433,16 @@ class CognitiveAimModel(nn.Module):
         """Curiosity draws [(eps [B,192], noise [B,768]), ...] -> pinned staging -> the fixed device buffers the
         (possibly graph-captured) curiosity kernel reads."""
         k, B = len(draws), draws[0][0].shape[0]
-        if slot["eps"] is None or slot["eps"].shape[1] < B:
+        if slot["eps"] is None or slot["eps"].shape[1] != B:
             slot["eps"] = torch.empty(_MAX_CURIOSITY_RUNS, B, 192).pin_memory()
             slot["noise"] = torch.empty(_MAX_CURIOSITY_RUNS, B, _D).pin_memory()
         for j, (eps, noise) in enumerate(draws):
-            slot["eps"][j, :B].copy_(eps)
-            slot["noise"][j, :B].copy_(noise)
-        ws["cur_eps"][:k].copy_(slot["eps"][:k, :B], non_blocking=True)
-        ws["cur_noise"][:k].copy_(slot["noise"][:k, :B], non_blocking=True)
+            slot["eps"][j].copy_(eps)
+            slot["noise"][j].copy_(noise)
+        # SM-side reads of the pinned staging area (ops.fetch_pinned), not cudaMemcpyAsync: these few hundred KB must not
+        # wait on the H2D copy engine behind the application's upload of the next image batch
+        ops.fetch_pinned(ws["cur_eps"][:k], slot["eps"][:k])
+        ops.fetch_pinned(ws["cur_noise"][:k], slot["noise"][:k])
 
     @staticmethod
     def _check_images(images):
@@ -661,8 +663,8 @@ class CognitiveAimModel(nn.Module):
         slot["b"].copy_(tmp.bias.detach())
         self._stage_draws(ws, slot, draws)
         ws["mask_in"].copy_(mask, non_blocking=True)
-        ws["tmpw"].copy_(slot["w"], non_blocking=True)
-        ws["tmpb"].copy_(slot["b"], non_blocking=True)
+        ops.fetch_pinned(ws["tmpw"], slot["w"])
+        ops.fetch_pinned(ws["tmpb"], slot["b"])
         slot["event"].record()
         ws["exif_in"].copy_(exif, non_blocking=True)
         ws["cam_in"].copy_(cam, non_blocking=True)

@@ -172,6 +172,21 @@ def focal_input(tokens, pe, rowscale, xin, B, N, D):
     return xin
 
 
+def fetch_pinned(dst, src_pinned):
+    """dst (CUDA fp32) <- src_pinned (pinned CPU fp32, contiguous, same numel) through an SM-side read of host memory:
+    never queues behind a bulk upload on the H2D copy engine (csrc/rowops.cu)."""
+    import ctypes as C
+    _req(dst, torch.float32, "dst")
+    if src_pinned.is_cuda or not src_pinned.is_pinned() or src_pinned.dtype != torch.float32:
+        raise ValueError("fetch_pinned expects a pinned fp32 CPU tensor")
+    if not (dst.is_contiguous() and src_pinned.is_contiguous()) or dst.numel() != src_pinned.numel():
+        raise ValueError("fetch_pinned expects contiguous tensors of equal size")
+    e0 = _begin()
+    check(_lib.load().ca_fetch_pinned_f32(ptr(dst), C.c_void_p(src_pinned.data_ptr()), dst.numel(), stream_ptr()),
+          "ca_fetch_pinned_f32")
+    _end(e0, "small", 1)
+
+
 def rowstats_merge(pm, ps, weight, rmax, rinv, wtab=None):
     rows, P = pm.numel() // pm.shape[-1], pm.shape[-1]
     e0 = _begin()

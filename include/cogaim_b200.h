@@ -82,6 +82,11 @@ int ca_layernorm(const float* x, const float* gamma, const float* beta, void* ou
 int ca_focal_input(const float* tokens, const float* pe, const float* rowscale, uint16_t* xin, int B, int N, int D,
                    void* stream);
 
+/* dst[0..n) (device) = h_src_pinned[0..n) (PAGE-LOCKED host memory), read by the SMs over PCIe instead of by the copy
+ * engine: the per-call inputs of src/model.py:609, :744, :1421 (Gaussian draws, fresh projection; a few hundred KB) must
+ * not queue on the H2D copy engine behind the application's bulk image upload.  Fails for pageable memory. */
+int ca_fetch_pinned_f32(float* dst, const float* h_src_pinned, size_t n, void* stream);
+
 /* Focal / guidance vector stages (fp32) ---------------------------------------------------------- */
 /* Merge the per-64-column partials of CA_EPI_ROWSTATS: rmax[r] = max, rinv[r] = (weight ? weight[r] : 1) / sumexp,
  * wtab[r, s] = exp2(pm[r, s] - rmax[r]) * rinv[r]; any of the three outputs may be null (not all).
