@@ -31,6 +31,7 @@ CFG = {"model": {"cognitive_modules": ["ambient_stream", "iterative_focal_stream
 INSTRUCTIONS = ["center", "left", "right", "top", "bottom", "top-left", "top-right", "bottom-left", "bottom-right"]
 # algorithmic FLOPs per image (backbone + focal Q|K projection and one QK^T x3)
 ALGO_GFLOP_BY_SIZE = {224: 48.4, 518: 321.5, 1036: 2218.0}
+ALGO_GFLOP_BACKBONE = {224: 46.32, 518: 303.15, 1036: 2041.0}  # --workload backbone (BASELINE.json configs[2])
 ALGO_GFLOP_PER_IMAGE = 321.5
 METRIC = "images/sec at 518x518 bf16"
 
@@ -176,7 +177,15 @@ def run_candidate(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    backbone_only = args.workload == "backbone"
+
     def step(i, imgs):
+        if backbone_only:
+            # BASELINE.json configs[2] (eval_configs/baseline_dinov2_config.yaml): the reference has no functional
+            # backbone-only depth path, so this is `Dinov2Model(images).last_hidden_state`;
+            # the per-image result handed back is the CLS row
+            cls = model.backbone_tokens(imgs)[:, 0]
+            return cls, cls[:, :1], cls[:, :1]
         torch.manual_seed(11)
         return model.forward_with_guidance(imgs, ex, INSTRUCTIONS[i % 9], return_attention=True)
 
@@ -218,8 +227,8 @@ def run_candidate(args):
     # ---- end to end through the public API with HOST buffers (pinned fp32 images in, outputs back to host) ----
     copy_stream = torch.cuda.Stream(device=dev)
     stage = [torch.empty_like(dev_imgs[0]) for _ in range(2)]
-    out_host = [torch.empty(B, 1).pin_memory(), torch.empty(B, 1).pin_memory(),
-                torch.empty(B, (S // 14) ** 2).pin_memory()]
+    out_host = [torch.empty(B, 768 if backbone_only else 1).pin_memory(), torch.empty(B, 1).pin_memory(),
+                torch.empty(B, 1 if backbone_only else (S // 14) ** 2).pin_memory()]
 
     def e2e_loop(n):
         ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -272,16 +281,19 @@ def run_candidate(args):
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"configs[1]: experiment_B full cognitive model, guided forward, {S}x{S}, "
-                               f"batch {B}/GPU, 9 instructions cycled, random-init weights (seed 0)",
+        "config": {"workload": (f"configs[2]: baseline_dinov2 backbone only (DINOv2 ViT-B/14 last_hidden_state), {S}x{S}, "
+                                f"batch {B}/GPU, random-init weights (seed 0)") if backbone_only else
+                               (f"configs[1]: experiment_B full cognitive model, guided forward, {S}x{S}, "
+                                f"batch {B}/GPU, 9 instructions cycled, random-init weights (seed 0)"),
                    "batch_per_gpu": B, "global_batch": B * world, "image_size": S, "parallelism": f"batch-shard x{world}",
                    "l2": f"{n_sets} rotating resident input batches (3 x {B * 3 * S * S * 4 / 1e6:.0f} MB) + ~1 GB of "
                          "activations per step: working set > 126 MB L2"},
         "e2e": {"value": B * world * args.steps / e2e_s, "unit": "images/s",
-                "h2d_bytes_per_step": B * 3 * S * S * 4 + 64 * 768 * 4 + 64 * 4,
-                "d2h_bytes_per_step": B * (2 + (S // 14) ** 2) * 4,
-                "note": "pinned fp32 host images -> H2D on a copy stream (double-buffered) -> forward_with_guidance -> "
-                        "depth/conf/heatmap D2H, wall clock incl. all copies"},
+                "h2d_bytes_per_step": B * 3 * S * S * 4 + (0 if backbone_only else 64 * 768 * 4 + 64 * 4),
+                "d2h_bytes_per_step": B * (770 if backbone_only else 2 + (S // 14) ** 2) * 4,
+                "note": "pinned fp32 host images -> H2D on a copy stream (double-buffered) -> %s D2H, wall clock incl. all "
+                        "copies" % ("backbone_tokens -> CLS rows" if backbone_only else
+                                    "forward_with_guidance -> depth/conf/heatmap")},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
@@ -299,7 +311,7 @@ def run_candidate(args):
         "kernel_breakdown_note": "second pass of the same steps launched eagerly with per-launch CUDA events; `value` is "
                                  "the CUDA-graph replay of the same launch sequence (use_cuda_graphs=%s)" % model.use_cuda_graphs,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not backbone_only:
         r = cpu_reference(steps=3, warmup=1, images_per_step=2)
         line["cpu_baseline"] = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port",
                                 "sample": "3 timed + 1 warm-up guided forwards of 2 synthetic 518x518 images (oracle "
@@ -319,9 +331,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--image-size", type=int, default=518, choices=sorted(ALGO_GFLOP_BY_SIZE),
                     help="sweep configs of BASELINE.json (224 / 1036); the headline metric is quoted at 518")
+    ap.add_argument("--workload", default="guided", choices=["guided", "backbone"],
+                    help="guided = configs[1] (default, the headline); backbone = configs[2] (DINOv2 tokens only)")
     args = ap.parse_args()
     global S, ALGO_GFLOP_PER_IMAGE, METRIC
-    S, ALGO_GFLOP_PER_IMAGE = args.image_size, ALGO_GFLOP_BY_SIZE[args.image_size]
+    S = args.image_size
+    ALGO_GFLOP_PER_IMAGE = (ALGO_GFLOP_BACKBONE if args.workload == "backbone" else ALGO_GFLOP_BY_SIZE)[S]
     METRIC = f"images/sec at {S}x{S} bf16"
     args.warmup = max(args.warmup, 3) if args.impl == "candidate" else args.warmup
     if args.impl == "reference":

@@ -34,7 +34,7 @@ _D = 768
 _HEADS = 12
 _LAYERS = 12
 _MLP = 3072
-_POOL_SPLITS = 8
+_POOL_SPLITS = 32  # 1024 CTAs at B = 32: the 8-way split (256 CTAs) reached 39 % of the HBM rate (profiles/r01e_bw_kernels.md)
 _MAX_CURIOSITY_RUNS = 3
 
 
@@ -422,7 +422,7 @@ class CognitiveAimModel(nn.Module):
         ring = getattr(self, "_pinned_ring", None)
         if ring is None:
             ring = {"slots": [{"w": torch.empty(64, _D).pin_memory(), "b": torch.empty(64).pin_memory(),
-                               "eps": None, "noise": None, "event": torch.cuda.Event()} for _ in range(4)], "next": 0}
+                               "draws": {}, "event": torch.cuda.Event()} for _ in range(4)], "next": 0}
             self._pinned_ring = ring
         slot = ring["slots"][ring["next"]]
         ring["next"] = (ring["next"] + 1) % len(ring["slots"])
@@ -433,16 +433,19 @@ class CognitiveAimModel(nn.Module):
         """Curiosity draws [(eps [B,192], noise [B,768]), ...] -> pinned staging -> the fixed device buffers the
         (possibly graph-captured) curiosity kernel reads."""
         k, B = len(draws), draws[0][0].shape[0]
-        if slot["eps"] is None or slot["eps"].shape[1] != B:
-            slot["eps"] = torch.empty(_MAX_CURIOSITY_RUNS, B, 192).pin_memory()
-            slot["noise"] = torch.empty(_MAX_CURIOSITY_RUNS, B, _D).pin_memory()
+        # one pinned pair per batch size, kept for the life of the model: a kernel reads them asynchronously, so they
+        # must never go back to the host allocator while a read may be in flight (the slot's event guards their REUSE)
+        bufs = slot["draws"].get(B)
+        if bufs is None:
+            bufs = slot["draws"][B] = (torch.empty(_MAX_CURIOSITY_RUNS, B, 192).pin_memory(),
+                                       torch.empty(_MAX_CURIOSITY_RUNS, B, _D).pin_memory())
         for j, (eps, noise) in enumerate(draws):
-            slot["eps"][j].copy_(eps)
-            slot["noise"][j].copy_(noise)
+            bufs[0][j].copy_(eps)
+            bufs[1][j].copy_(noise)
         # SM-side reads of the pinned staging area (ops.fetch_pinned), not cudaMemcpyAsync: these few hundred KB must not
         # wait on the H2D copy engine behind the application's upload of the next image batch
-        ops.fetch_pinned(ws["cur_eps"][:k], slot["eps"][:k])
-        ops.fetch_pinned(ws["cur_noise"][:k], slot["noise"][:k])
+        ops.fetch_pinned(ws["cur_eps"][:k], bufs[0][:k])
+        ops.fetch_pinned(ws["cur_noise"][:k], bufs[1][:k])
 
     @staticmethod
     def _check_images(images):
