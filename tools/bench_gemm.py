@@ -2,7 +2,10 @@
 import sys
 import torch
 sys.path.insert(0, '/root/repo')
-from cognitive_aim_depth_estimation_b200 import ops
+from cognitive_aim_depth_estimation_b200 import ops, _lib
+import os, pathlib
+if os.environ.get("CA_LIB_OVERRIDE"):
+    _lib.LIB_PATH = pathlib.Path(os.environ["CA_LIB_OVERRIDE"])  # tooling only: same-box A/B of two builds
 M = 32 * 1370
 dev = 'cuda'
 shapes = [("qkv", 2304, 768, ops.EPI_BIAS_BF16), ("proj", 768, 768, ops.EPI_RESID_F32),
