@@ -113,6 +113,26 @@ __device__ __forceinline__ float ffma_sat(float a, float b, float c) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// explicit shared-memory accesses: through a generic pointer the compiler emits LD.E / ST.E (generic address path,
+// tracked on the long scoreboard) where LDS / STS would do
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128f(uint32_t saddr, float4 v) {
+  sts128(saddr, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+}
+__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
+  const uint4 v = lds128(saddr);
+  return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

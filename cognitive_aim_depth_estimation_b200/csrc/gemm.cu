@@ -187,6 +187,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
     // modified / written with lanes laid out as 8 rows x 4 x 16 B: every global access moves full sectors.
     const int lrow = lane >> 3;  // row within a group of 4 (8 passes cover the warp's 32 rows)
     const int seg = lane & 7;    // 16-byte piece of the 128-byte chunk row
+    const uint32_t stage_s = smem_u32(stage);  // explicit .shared accesses (LDS / STS instead of generic LD.E / ST.E)
     if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16) {
 #pragma unroll 1
       for (int c = 0; c < kSpan; c += 64) {
@@ -218,7 +219,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
               w.y = pack_bf16x2(a[2], a[3]);
               w.z = pack_bf16x2(a[4], a[5]);
               w.w = pack_bf16x2(a[6], a[7]);
-              *reinterpret_cast<uint4*>(stage + epi_off(lane, 4 * hh + j)) = w;
+              sts128(stage_s + epi_off(lane, 4 * hh + j), w);
             }
           }
         }
@@ -230,7 +231,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
           for (int i = 0; i < 8; ++i) {
             const int rr = lrow + 4 * i;
             const int grow = mt * BM + quad * 32 + rr;
-            const uint4 w = *reinterpret_cast<const uint4*>(stage + epi_off(rr, seg));
+            const uint4 w = lds128(stage_s + epi_off(rr, seg));
             if (grow < p.M) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(grow) * p.ldo) = w;
           }
           __syncwarp();
@@ -256,9 +257,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
         for (int j = 0; j < 8; ++j) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
           const float4 l4 = __ldg(reinterpret_cast<const float4*>(p.ls + col) + j);
-          *reinterpret_cast<float4*>(stage + epi_off(lane, j)) =
+          sts128f(stage_s + epi_off(lane, j),
               make_float4(l4.x * (__uint_as_float(v[4 * j + 0]) + t.x), l4.y * (__uint_as_float(v[4 * j + 1]) + t.y),
-                          l4.z * (__uint_as_float(v[4 * j + 2]) + t.z), l4.w * (__uint_as_float(v[4 * j + 3]) + t.w));
+                          l4.z * (__uint_as_float(v[4 * j + 2]) + t.z), l4.w * (__uint_as_float(v[4 * j + 3]) + t.w)));
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -286,7 +287,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
               a.z += t.z;
               a.w += t.w;
             }
-            *reinterpret_cast<float4*>(stage + epi_off(lane, j)) = a;
+            sts128f(stage_s + epi_off(lane, j), a);
           }
           __syncwarp();
           float* obase = reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride + col + seg * 4;
@@ -294,7 +295,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
           for (int i = 0; i < 8; ++i) {
             const int rr = lrow + 4 * i;
             const int grow = mt * BM + quad * 32 + rr;
-            const float4 a = *reinterpret_cast<const float4*>(stage + epi_off(rr, seg));
+            const float4 a = lds128f(stage_s + epi_off(rr, seg));
             if (grow < p.M) {
               if constexpr (EPI == EPI_PATCH_F32) {
                 const int img = grow / p.patches_per_img;
