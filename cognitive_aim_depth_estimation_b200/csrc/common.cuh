@@ -373,12 +373,13 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t ra
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// The same arrive WITHOUT release semantics.  A cluster-scope release compiles to MEMBAR.ALL.GPU + ERRBAR: the thread waits
-// until every global store it has issued is acknowledged.  Where the barrier only says "my tcgen05.ld of this TMEM
-// region have completed" (tcgen05.wait::ld + tcgen05.fence::before_thread_sync already order those) and no generic-proxy
-// data is handed over, the relaxed form is sufficient and does not drain the epilogue's result stores.
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// The same arrive with CTA-scope (default) release semantics on the remote barrier — the form CUTLASS's
+// ClusterBarrier::arrive(cta_id) emits.  A CLUSTER-scope release compiles to MEMBAR.ALL.GPU + ERRBAR: the thread waits until
+// every global store it has issued is acknowledged.  Where the barrier only says "my tcgen05.ld of this TMEM region have
+// completed" (tcgen05.wait::ld + tcgen05.fence::before_thread_sync already order those) and no generic-proxy data is
+// handed to the other CTA, that drain is pure loss.  (`.relaxed.cluster` measures the same; this is the proven form.)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion is signalled on an mbarrier that may live in the PEER CTA (cluster address)
 __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* tm, uint32_t mbar_cluster_addr, int c0,

@@ -24,7 +24,7 @@
 #include <stdlib.h>
 
 #ifndef CA_GEMM_RELEASE_ARRIVE
-#define CA_GEMM_RELEASE_ARRIVE 0  // 1 = the former release-ordered accumulator hand-back (A/B only)
+#define CA_GEMM_RELEASE_ARRIVE 0  // 1 = the former cluster-scope-release accumulator hand-back (A/B only)
 #endif
 
 namespace ca {
@@ -588,10 +588,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #if CA_GEMM_RELEASE_ARRIVE
       if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&acc_empty[acc]), 0));
 #else
-      // "this warp has read its part of the accumulator out of TMEM": no memory is published through this barrier, so
-      // the arrive is relaxed (the release form made every epilogue warp wait for its result stores to be acknowledged:
-      // 18 % of the fc1 kernel's warp samples sat on the resulting MEMBAR.ALL.GPU / ERRBAR)
-      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_cluster(smem_u32(&acc_empty[acc]), 0));
+      // "this warp has read its part of the accumulator out of TMEM": no memory is published to the other CTA through
+      // this barrier, so the arrive carries CTA-scope release only (the cluster-scope release made every epilogue warp
+      // wait for its result stores to be acknowledged: 18 % of the fc1 kernel's warp samples sat on the resulting
+      // MEMBAR.ALL.GPU / ERRBAR)
+      if (lane == 0) mbar_arrive_remote(mapa_cluster(smem_u32(&acc_empty[acc]), 0));
 #endif
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
