@@ -106,55 +106,63 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(half * kSpan);
 
   if constexpr (EPI == EPI_ROWSTATS) {
-    // pass 1: max ; pass 2: sum exp2(s - max).  TMEM re-read is cheaper than holding kSpan registers.
-    float mx = -INFINITY;
+    // Softmax statistics per 64-column span (the granularity ca_rowstats_merge / ca_colsum_e work in): this warp owns
+    // kSpan / 64 of them (one with 128-wide tiles, two with the 256-wide tiles of the CTA-pair kernel).
+    // pass 1: max ; pass 2: sum exp2(s - max).  TMEM re-read is cheaper than holding the span in registers.
+    constexpr int kSub = kSpan / 64;
+#pragma unroll 1
+    for (int sub = 0; sub < kSub; ++sub) {
+      const int col_sub = col_base + sub * 64;
+      const uint32_t taddr_sub = taddr + static_cast<uint32_t>(sub * 64);
+      float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < kSpan; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(taddr + c, v);
-      tmem_ld_wait();
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr_sub + c, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float s = __uint_as_float(v[j]) * p.scale_log2;
-        if (col_base + c + j < p.N) mx = fmaxf(mx, s);
-      }
-    }
-    float sum = 0.f;
-    // optional: keep the span-relative exponentials E = exp2(s - span max) as fp16 so that the column sums of the
-    // softmax are a bandwidth pass over E instead of a second Q K^T (ca_colsum_e)
-    __half* erow = p.out == nullptr ? nullptr
-                                    : reinterpret_cast<__half*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride +
-                                          static_cast<size_t>(row) * p.ldo + col_base;
-#pragma unroll
-    for (int c = 0; c < kSpan; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(taddr + c, v);
-      tmem_ld_wait();
-      float ev[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float s = __uint_as_float(v[j]) * p.scale_log2;
-        ev[j] = (col_base + c + j < p.N) ? fast_exp2(s - mx) : 0.f;
-        sum += ev[j];
-      }
-      if (erow != nullptr && row_ok && col_base + c < p.ldo) {  // ldo is a multiple of 64: whole 32-column pieces
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 w;
-          __half2 h0 = __floats2half2_rn(ev[j + 0], ev[j + 1]), h1 = __floats2half2_rn(ev[j + 2], ev[j + 3]);
-          __half2 h2 = __floats2half2_rn(ev[j + 4], ev[j + 5]), h3 = __floats2half2_rn(ev[j + 6], ev[j + 7]);
-          w.x = *reinterpret_cast<uint32_t*>(&h0);
-          w.y = *reinterpret_cast<uint32_t*>(&h1);
-          w.z = *reinterpret_cast<uint32_t*>(&h2);
-          w.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(erow + c + j) = w;
+        for (int j = 0; j < 32; ++j) {
+          const float s = __uint_as_float(v[j]) * p.scale_log2;
+          if (col_sub + c + j < p.N) mx = fmaxf(mx, s);
         }
       }
-    }
-    if (row_ok) {
-      const size_t o = (static_cast<size_t>(b) * p.M + row) * p.partials + nt * 2 + half;
-      p.part_a[o] = mx;
-      p.part_b[o] = sum;
+      float sum = 0.f;
+      // optional: keep the span-relative exponentials E = exp2(s - span max) as fp16 so that the column sums of the
+      // softmax are a bandwidth pass over E instead of a second Q K^T (ca_colsum_e)
+      __half* erow = p.out == nullptr ? nullptr
+                                      : reinterpret_cast<__half*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride +
+                                            static_cast<size_t>(row) * p.ldo + col_sub;
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr_sub + c, v);
+        tmem_ld_wait();
+        float ev[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float s = __uint_as_float(v[j]) * p.scale_log2;
+          ev[j] = (col_sub + c + j < p.N) ? fast_exp2(s - mx) : 0.f;
+          sum += ev[j];
+        }
+        if (erow != nullptr && row_ok && col_sub + c < p.ldo) {  // ldo is a multiple of 64: whole 32-column pieces
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 w;
+            __half2 h0 = __floats2half2_rn(ev[j + 0], ev[j + 1]), h1 = __floats2half2_rn(ev[j + 2], ev[j + 3]);
+            __half2 h2 = __floats2half2_rn(ev[j + 4], ev[j + 5]), h3 = __floats2half2_rn(ev[j + 6], ev[j + 7]);
+            w.x = *reinterpret_cast<uint32_t*>(&h0);
+            w.y = *reinterpret_cast<uint32_t*>(&h1);
+            w.z = *reinterpret_cast<uint32_t*>(&h2);
+            w.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(erow + c + j) = w;
+          }
+        }
+      }
+      if (row_ok) {
+        const size_t o = (static_cast<size_t>(b) * p.M + row) * p.partials + nt * (BN / 64) + half * kSub + sub;
+        p.part_a[o] = mx;
+        p.part_b[o] = sum;
+      }
     }
     return;
   } else if constexpr (EPI == EPI_COLSUM) {
@@ -651,7 +659,12 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   CA_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 elements (16 B) for TMA");
   CA_REQUIRE(a.K <= a.lda && a.K <= a.ldw, "gemm: K exceeds a leading dimension");
   const bool stats = (a.epilogue == EPI_ROWSTATS || a.epilogue == EPI_COLSUM);
-  const int bn = stats ? 128 : 256;
+  // dense epilogues and the row-statistics pass run on CTA pairs (cta_group::2, 256 x 256 pair tiles) unless
+  // CA_GEMM_1CTA is set; the (test-only) column-sum recompute pass keeps the single-CTA 128 x 128 kernel, whose operand
+  // traffic (256 B/clk of fill + reads against a 128 B/clk shared-memory port) caps it near half the tensor rate
+  static const bool force_1cta = getenv("CA_GEMM_1CTA") != nullptr;
+  const bool pair = !force_1cta && a.epilogue != EPI_COLSUM;
+  const int bn = (stats && !pair) ? 128 : 256;
   if (!stats) {
     CA_REQUIRE(a.N % 32 == 0, "gemm: N must be a multiple of 32 for the dense epilogues");
     CA_REQUIRE((a.epilogue != EPI_BIAS_BF16 && a.epilogue != EPI_GELU_BF16) || a.N % 64 == 0,
@@ -670,11 +683,6 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     CA_REQUIRE(a.epilogue != EPI_ROWSTATS || a.out == nullptr || (a.ldo % 64 == 0 && a.ldo >= a.N),
                "gemm: the exponential matrix needs a leading dimension that is a multiple of 64 and >= N");
   }
-
-  // dense epilogues run on CTA pairs (cta_group::2) unless CA_GEMM_1CTA is set; the statistics epilogues keep the
-  // single-CTA 128 x 128 kernel
-  static const bool force_1cta = getenv("CA_GEMM_1CTA") != nullptr;
-  const bool pair = !stats && !force_1cta;
 
   CUtensorMap ta, tw;
   const long long abs = a.batch > 1 ? a.a_batch_stride : static_cast<long long>(a.M) * a.lda;
@@ -698,6 +706,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   ka.K = a.K;
   ka.m_tiles = pair ? (a.M + 2 * BM - 1) / (2 * BM) : (a.M + BM - 1) / BM;  // pair kernel: 256-row tiles
   ka.n_tiles = (a.N + bn - 1) / bn;
+  if (stats && bn == 128) ka.n_tiles = (ka.n_tiles + 1) & ~1;  // every one of the P = 4 ceil(N / 256) slots gets written
   ka.total_tiles = ka.m_tiles * ka.n_tiles * a.batch;
   ka.w_batched = wb ? 1 : 0;
   ka.out = a.out;
@@ -723,6 +732,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
       case EPI_RESID_F32: return launch_inst2<EPI_RESID_F32>(ta, tw, tx, ka, stream);
       case EPI_PATCH_F32: return launch_inst2<EPI_PATCH_F32>(ta, tw, tx, ka, stream);
       case EPI_F32: return launch_inst2<EPI_F32>(ta, tw, tx, ka, stream);
+      case EPI_ROWSTATS: return launch_inst2<EPI_ROWSTATS>(ta, tw, tx, ka, stream);
       default: return invalid("gemm: unknown epilogue");
     }
   }

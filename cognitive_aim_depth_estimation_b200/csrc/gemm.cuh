@@ -43,8 +43,8 @@ struct GemmArgs {
   const float* col_rinv;           // COLSUM: [batch, N] weight_i / sumexp_i
 };
 
-// P (partials per row) for the stats epilogues = 2 * ceil(N / 128).
-inline int gemm_stats_partials(int N) { return 2 * ((N + 127) / 128); }
+// P (partials per row) for the stats epilogues: one per 64-column span of the 256-wide pair tiles = 4 * ceil(N / 256).
+inline int gemm_stats_partials(int N) { return 4 * ((N + 255) / 256); }
 
 int gemm_launch(const GemmArgs& args, cudaStream_t stream);
 

@@ -79,7 +79,8 @@ def _req(t, dtype, name):
 
 
 def stats_partials(n: int) -> int:
-    return 2 * ((n + 127) // 128)
+    """P: per-row partial slots of the statistics epilogues = one per 64-column span of the 256-wide tiles."""
+    return 4 * ((n + 255) // 256)
 
 
 def gemm(A, W, epilogue, out=None, *, M=None, N=None, K=None, lda=None, ldw=None, batch=1, a_batch_stride=0,

@@ -52,7 +52,8 @@ int ca_device_check(int device);            /* CA_STATUS_OK iff `device` is comp
 /* Dense contraction on tcgen05 tensor cores --------------------------------------------------- */
 /* C[b] = epilogue(A[b] (M x K, lda) * W[b] (N x K, ldw)^T), bf16 operands, fp32 TMEM accumulators.
  * w_batch_stride == 0 shares W across the batch.  Unused epilogue operands may be NULL.
- * For CA_EPI_ROWSTATS/COLSUM the per-row partial buffers have P = 2*ceil(N/128) entries per row. */
+ * For CA_EPI_ROWSTATS/COLSUM the per-row partial buffers have P = 4*ceil(N/256) entries per row (one per 64-column
+ * span of the 256-wide tiles; spans past N hold max = -inf, sum = 0). */
 int ca_gemm_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K, int lda, int ldw, int batch,
                  long long a_batch_stride, long long w_batch_stride, int epilogue, void* out, int ldo,
                  long long out_batch_stride, const float* bias, const float* ls, const float* pos,
