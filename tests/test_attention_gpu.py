@@ -25,3 +25,24 @@ def test_attention_matches_fp32(cuda_device, B, T, H, scale):
     err = (out.float() - ref).abs().max().item()
     rel = ((out.float() - ref).norm() / ref.norm()).item()
     assert rel < 8e-3, (rel, err)
+
+
+def test_attention_reference_jumps_mid_sequence(cuda_device):
+    """Keys whose scores dwarf everything seen so far arrive late in the sequence (x 40 from token 700 on, x 0.02 again
+    from 1000 on): the running reference of the softmax must be raised — lazily, at the next step, or at once with the
+    step redone when it is off by more than 2^24 — without losing the earlier contributions."""
+    from cognitive_aim_depth_estimation_b200 import ops
+    B, T, H = 1, 1370, 4
+    g = torch.Generator().manual_seed(99)
+    qkv = torch.randn(B * T, 3 * H * 64, generator=g)
+    k = qkv[:, H * 64: 2 * H * 64]
+    k[700:1000] *= 40.0
+    k[1000:] *= 0.02
+    qkv = qkv.to(cuda_device).bfloat16()
+    out = torch.full((B * T, H * 64), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, T, H)
+    torch.cuda.synchronize()
+    ref = _ref(qkv, B, T, H)
+    assert torch.isfinite(out.float()).all()
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    assert rel < 8e-3, rel
