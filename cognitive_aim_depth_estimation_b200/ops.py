@@ -348,7 +348,7 @@ def curiosity(weights, *, tokens, tokens_per_img, eps, noise, reward_raw, reward
     check(_lib.load().ca_curiosity(C.byref(weights), ptr(tokens), tokens_per_img, ptr(eps), ptr(noise), ptr(reward_raw),
                                    ptr(reward), ptr(history), 0 if history is None else history.numel(),
                                    ptr(history_pointer), B, stream_ptr()), "ca_curiosity")
-    _end(e0, "heads", 1 if history is None else 2)
+    _end(e0, "curiosity", 1 if history is None else 2)
 
 
 def curiosity_modulation(weights, reward, lo, hi, cur_weight, B, n_iters, mod_hidden):
@@ -359,7 +359,7 @@ def curiosity_modulation(weights, reward, lo, hi, cur_weight, B, n_iters, mod_hi
     e0 = _begin()
     check(_lib.load().ca_curiosity_modulation(C.byref(weights), ptr(reward), float(lo), float(hi), ptr(cur_weight), B,
                                               n_iters, mod_hidden, stream_ptr()), "ca_curiosity_modulation")
-    _end(e0, "heads", 1)
+    _end(e0, "curiosity", 1)
 
 
 def focal_value(*, tok_partial, pe_partial, splits, wv, bv, proj_w0, proj_b0, proj_w1, proj_b1, feat_out, it, n_iters,
