@@ -86,3 +86,37 @@ def test_jpeg_to_tokens_matches_demo_chain(cuda_device):
     # a ~1 % input perturbation (0.009 on unit-variance pixels) through the random-init ViT stays a ~1 % token perturbation
     rel = ((t_got - t_want).norm() / t_want.norm()).item()
     assert rel < 3e-2, rel
+
+
+def test_predict_like_demo_example(cuda_device):
+    """examples/predict_like_demo.py: demo.py's per-image flow (decode, transform, default EXIF, guided call, overlay) for
+    the 9 instructions on one synthetic JPEG; depth against the oracle on the PIL / torchvision path of the same file."""
+    import importlib.util
+    import os
+    from torchvision import transforms
+    spec = importlib.util.spec_from_file_location(
+        "predict_like_demo", os.path.join(os.path.dirname(os.path.dirname(__file__)), "examples", "predict_like_demo.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sd = orc.build_state_dict(0)
+    p = mod.Predictor(sd, image_size=224)
+    data = _jpeg(_synthetic(480, 640, 7), 95, 0)
+    tf = transforms.Compose([transforms.Resize((224, 224)), transforms.ToTensor(),
+                             transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    x_ref = tf(Image.open(io.BytesIO(data)).convert("RGB")).unsqueeze(0)
+    exif = {k: v.cpu() for k, v in p.default_exif(1).items()}
+    tokens = orc.dinov2_tokens(sd, x_ref)
+    cells = set()
+    for ins in mod.INSTRUCTIONS:
+        torch.manual_seed(11)
+        ref = orc.forward_with_guidance(sd, None, exif, ins, tokens=tokens, update_history=False)
+        torch.manual_seed(11)
+        depth, conf, meta = p.predict(data, ins, overlay_size=(48, 64))
+        # two decoders (<= 5 LSB apart) in front of a random-init network: 3 % on the depth, same confidence
+        assert abs(depth - float(ref["depth"])) / float(ref["depth"]) <= 3e-2, (ins, depth, float(ref["depth"]))
+        assert abs(conf - float(ref["confidence"])) <= 1e-2
+        assert meta["overlay"].shape == (48, 64) and 0.0 <= float(meta["overlay"].min()) and float(meta["overlay"].max()) <= 1.0
+        cells.add(meta["attention_cell"])
+    assert len(cells) >= 7  # the instructions steer the attention to different cells
+    d0, c0, m0 = p.predict(data, None)  # un-guided call of demo.py:349-352
+    assert d0 > 0 and 0 < c0 < 1 and m0["instruction"] is None
