@@ -162,9 +162,9 @@ def run_candidate(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     B = args.batch
+    torch.manual_seed(0)  # the reference's random init (create_model replays its construction order: init.py)
     model = create_model(CFG, {"num_cameras": 71}, device=dev)
-    model.load_state_dict(orc.build_state_dict(0))
-    model.validate_inputs = False
+    # default API path: input validation stays ON (the camera_idx range check runs inside the heads kernel, no sync)
     # three distinct resident input batches (3 x 103 MB fp32) rotate so no step re-reads an L2-resident input;
     # per-step activations (~1 GB) exceed the 126 MB L2 on their own
     n_sets = 3

@@ -35,7 +35,8 @@ class HeadsInputs(C.Structure):
     """ca_heads_inputs (include/cogaim_b200.h)."""
     _fields_ = [("tokens", C.c_void_p), ("tokens_per_img", C.c_int), ("focal_feat", C.c_void_p),
                 ("pool_partial", C.c_void_p), ("pool_splits", C.c_int), ("tmp_w", C.c_void_p), ("tmp_b", C.c_void_p),
-                ("pooled_out", C.c_void_p), ("exif", C.c_void_p), ("camera_idx", C.c_void_p)]
+                ("pooled_out", C.c_void_p), ("exif", C.c_void_p), ("camera_idx", C.c_void_p),
+                ("num_cameras", C.c_int), ("fault", C.c_void_p)]
 
 
 class FocalValueArgs(C.Structure):

@@ -34,6 +34,9 @@
 
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 #include <type_traits>
 
 namespace ca {
@@ -113,7 +116,7 @@ struct AttnArgs {
   __nv_bfloat16* out;  // [B*T, H*64]
   int ldo;
   int stagger;     // cycles the second CTA of each SM waits before its first step
-  int* counter;    // [0] global work counter, [1] count of finished CTAs; both zero at launch, re-zeroed by the last CTA
+  int* counter;    // global work counter of THIS launch (zeroed on the launch stream just before the kernel)
   long long* dbg;  // CA_ATTN_DEBUG=1: per-CTA {cycles, smid}
 };
 
@@ -541,17 +544,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
 
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    // The last CTA to leave re-arms the work counter for the next launch (every claim of this launch has returned by
-    // then: a CTA only gets here after its scheduler drew the out-of-work sentinel), so launches — eager or replayed
-    // from a CUDA graph — need no host-side reset.
-    __threadfence();
-    if (atomicAdd(p.counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
-      p.counter[0] = 0;
-      p.counter[1] = 0;
-      __threadfence();
-    }
-  }
   if (p.dbg && threadIdx.x == 0) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -564,6 +556,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
   }
 }
 
+constexpr int kMaxDevices = 64;
+constexpr unsigned kCounterRing = 1024;
+struct DeviceState {
+  int* ring = nullptr;
+  int sms = 0;
+  std::atomic<unsigned> next{0};
+};
+DeviceState g_dev[kMaxDevices];
+std::mutex g_mu;
+
 }  // namespace
 
 int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, cudaStream_t stream) {
@@ -572,10 +574,18 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
   const int ld = 3 * H * kHeadDim;
   CUtensorMap tm_kv;
   CA_TRY(make_tmap_3d(&tm_kv, qkv, B, T, ld, ld, static_cast<uint64_t>(T) * ld, kSubK));
-  static bool configured = false;
-  if (!configured) {
-    CA_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
-    configured = true;
+  int dev = 0;
+  CA_CUDA(cudaGetDevice(&dev));
+  CA_REQUIRE(dev >= 0 && dev < kMaxDevices, "attention: device index out of range");
+  DeviceState& st = g_dev[dev];
+  {
+    // once per device: the > 48 KB shared-memory opt-in is per context, and so is the ring of work counters
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!st.ring) {
+      CA_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+      CA_CUDA(cudaDeviceGetAttribute(&st.sms, cudaDevAttrMultiProcessorCount, dev));
+      CA_CUDA(cudaMalloc(&st.ring, kCounterRing * sizeof(int)));
+    }
   }
   AttnArgs a;
   a.T = T;
@@ -588,18 +598,12 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
   a.ld = ld;
   a.out = out;
   a.ldo = H * kHeadDim;
-  const int grid = a.n_items < 2 * sm_count() ? a.n_items : 2 * sm_count();  // persistent: two CTAs per SM
-  // work counter + exit counter, self-resetting (launches on one device are serialised on a stream, see
-  // include/cogaim_b200.h); allocated on first use, per device
-  static int* d_counter[64] = {};
-  int dev = 0;
-  CA_CUDA(cudaGetDevice(&dev));
-  CA_REQUIRE(dev >= 0 && dev < 64, "attention: device index out of range");
-  if (!d_counter[dev]) {
-    CA_CUDA(cudaMalloc(&d_counter[dev], 2 * sizeof(int)));
-    CA_CUDA(cudaMemset(d_counter[dev], 0, 2 * sizeof(int)));
-  }
-  a.counter = d_counter[dev];
+  const int grid = a.n_items < 2 * st.sms ? a.n_items : 2 * st.sms;  // persistent: two CTAs per SM
+  // Every launch owns one slot of a per-device ring of work counters, zeroed on ITS stream right before the kernel (a
+  // memset node when the launch is captured into a graph): launches that overlap on different streams never share a
+  // counter, and a launch that died leaves nothing behind for the next one.
+  a.counter = st.ring + (st.next.fetch_add(1u) % kCounterRing);
+  CA_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), stream));
   static const int stagger = getenv("CA_ATTN_STAGGER") ? atoi(getenv("CA_ATTN_STAGGER")) : 0;
   a.stagger = stagger;
   static const bool want_dbg = getenv("CA_ATTN_DEBUG") != nullptr;

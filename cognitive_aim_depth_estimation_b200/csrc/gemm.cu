@@ -623,11 +623,11 @@ template <int EPI>
 int launch_inst2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tx, const GemmKernelArgs& ka,
                  cudaStream_t stream) {
   auto kern = gemm2_tcgen05_kernel<EPI>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static PerDeviceOnce configured;  // per instantiation and per device (the opt-in is per context)
+  CA_TRY(configured.run([&]() -> int {
     CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::kSmemBytes));
-    configured = true;
-  }
+    return 0;
+  }));
   const int max_clusters = sm_count() / 2;
   const int clusters = ka.total_tiles < max_clusters ? ka.total_tiles : max_clusters;
   kern<<<2 * clusters, kGemmThreads, Gemm2Cfg::kSmemBytes, stream>>>(ta, tw, tx, ka);
@@ -640,11 +640,11 @@ int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
                 cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tcgen05_kernel<BN, EPI>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static PerDeviceOnce configured;  // per instantiation and per device
+  CA_TRY(configured.run([&]() -> int {
     CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
+    return 0;
+  }));
   int grid = ka.total_tiles < sm_count() ? ka.total_tiles : sm_count();
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, tx, ka);
   CA_CUDA(cudaGetLastError());

@@ -55,7 +55,14 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const HeadsWeights
       s_in[1] = e[1];
       s_in[2] = logf(e[2] + 1.0f);
     }
+    // camera index checked HERE, not on the host: no device-to-host sync on the call path.  An index outside the
+    // embedding table is clamped (no out-of-bounds read) and reported through the fault word, which the host reads
+    // without synchronising (pinned memory) before its next call — nn.Embedding would have raised (src/model.py:491).
     long long cam = in.camera_idx[b];
+    if (in.num_cameras > 0 && (cam < 0 || cam >= in.num_cameras)) {
+      if (tid == 0 && in.fault) atomicOr(in.fault, 1);
+      cam = cam < 0 ? 0 : in.num_cameras - 1;
+    }
     for (int i = tid; i < 64; i += kHeadsThreads) s_b[i] = wt.cam_emb[cam * 64 + i];  // cat([camera, exif]) slot 0..63
     __syncthreads();
     dense(wt.exif_w0, wt.exif_b0, s_in, s_a, 3, 64, true);

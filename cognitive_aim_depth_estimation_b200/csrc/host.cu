@@ -107,14 +107,23 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t ro
   return make_tmap_bf16_sw128(out, base, 3, dims, strides, box);
 }
 
+int current_device() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  static std::mutex mu;
+  static int cached[64] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lock(mu);
+  if (cached[dev] == 0) {
+    int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
   }
-  return n;
+  return cached[dev];
 }
 
 }  // namespace ca

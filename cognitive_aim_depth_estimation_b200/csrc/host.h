@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 
 namespace ca {
@@ -45,6 +46,29 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t ro
 // residual epilogue's TMA reduce-add.
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
-int sm_count();
+int sm_count();         // SMs of the CURRENT device (cached per device)
+int current_device();   // cudaGetDevice, -1 on failure
+
+// One-time setup that is per CUDA context, not per process (cudaFuncSetAttribute opt-ins above 48 KB of shared memory):
+// `run(f)` calls f() the first time it is reached with a given device current, under a lock, and returns f's status
+// (0 = ok; a failure is retried on the next call).
+class PerDeviceOnce {
+ public:
+  template <class F>
+  int run(F&& f) {
+    const int dev = current_device();
+    if (dev < 0 || dev >= 64) return f();
+    const unsigned long long bit = 1ull << dev;
+    std::lock_guard<std::mutex> lock(mu_);
+    if (done_ & bit) return 0;
+    const int status = f();
+    if (status == 0) done_ |= bit;
+    return status;
+  }
+
+ private:
+  std::mutex mu_;
+  unsigned long long done_ = 0;
+};
 
 }  // namespace ca

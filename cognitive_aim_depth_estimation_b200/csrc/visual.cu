@@ -110,11 +110,11 @@ int focus_map_launch(const float* heat, int B, int g, int out_h, int out_w, floa
   CA_REQUIRE(B > 0 && g > 0, "focus_map: non-positive dimension");
   const int N = g * g;
   CA_REQUIRE(N <= 16384, "focus_map: grid larger than 128 x 128 is not supported");
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  CA_TRY(configured.run([&]() -> int {
     CA_CUDA(cudaFuncSetAttribute(focus_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4));
-    configured = true;
-  }
+    return 0;
+  }));
   focus_normalize_kernel<<<B, kVisThreads, N * sizeof(float), stream>>>(heat, norm, N);
   CA_CUDA(cudaGetLastError());
   if (out != nullptr) {

@@ -20,6 +20,7 @@ Differences that are deliberate:
 from __future__ import annotations
 
 import contextlib
+import functools
 import math
 import os
 from typing import Dict, Optional
@@ -29,6 +30,7 @@ import torch.nn as nn
 
 from . import ops, tables
 from .config import DEFAULT_COGNITIVE_MODULES, EffectiveConfig, effective_config
+from .init import reference_init_
 
 _D = 768
 _HEADS = 12
@@ -108,6 +110,20 @@ def _param_specs(cfg: EffectiveConfig):
     return s
 
 
+def _on_own_device(fn):
+    """Run a public entry point with the model's GPU as the current CUDA device: every ca_* launch goes to the CURRENT
+    device and torch.cuda.current_stream() is per device, so a model living on cuda:1 must not launch on cuda:0 just
+    because the caller never called torch.cuda.set_device(1)."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        dev = self._device()
+        if dev.type != "cuda":
+            return fn(self, *a, **k)  # argument checks first; _pack() then refuses: there is no CPU fallback
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapped
+
+
 def _register(root: nn.Module, dotted: str, tensor: torch.Tensor, buffer: bool):
     mod = root
     parts = dotted.split(".")
@@ -151,30 +167,18 @@ class CognitiveAimModel(nn.Module):
         self.use_ambient, self.use_focal = cfg.use_ambient, cfg.use_focal
         self.use_iterative, self.use_exif = cfg.use_iterative, cfg.use_exif
         self.target_fusion_dim = 768
-        gen = torch.Generator().manual_seed(0x5EED)
+        # Parameter tree by reference name; values come from reference_init_, which consumes the global CPU generator
+        # exactly like the reference's constructor: torch.manual_seed(s) + create_model(...) == the reference's weights.
         for name, shape, kind in _param_specs(cfg):
-            if kind == "w":
-                t = torch.empty(shape).normal_(0.0, 0.02, generator=gen).clamp_(-0.04, 0.04)
-            elif kind == "ones":
-                t = torch.ones(shape)
-            elif kind == "zeros":
-                t = torch.zeros(shape)
-            elif kind.startswith("const:"):
-                t = torch.full(shape, float(kind[6:]))
-            elif kind == "curw":
-                t = torch.tensor([0.4, 0.3, 0.3])
-            elif kind == "buf_zeros":
-                t = torch.zeros(shape)
-            elif kind == "buf_long":
-                t = torch.tensor(0)
-            else:
-                raise AssertionError(kind)
+            t = torch.tensor(0) if kind == "buf_long" else torch.zeros(shape)
             _register(self, name, t, buffer=kind.startswith("buf"))
+        reference_init_(dict(self.state_dict(keep_vars=True)), cfg)
         self._packed = None       # device-side packed weights (bf16 GEMM operands etc.)
         self._packed_key = None
         self._tables: Dict = {}   # per-grid tables (pos-embed, PE, centre bias, masks)
         self._ws: Dict = {}       # workspaces keyed by (B, S)
-        self.validate_inputs = True
+        self.validate_inputs = True   # camera_idx range faults (checked on the device) are raised at the next call
+        self._fault = None            # pinned int32 the heads kernel flags input faults in
         self.rng_replay_batch = None  # sharded runs: replay the reference's RNG draws at the GLOBAL batch size
         self.rng_replay_offset = 0    # ... and take this shard's rows of them
         # The ~110 launches of one forward are captured once per (batch, resolution, path) into a CUDA graph and
@@ -458,6 +462,7 @@ class CognitiveAimModel(nn.Module):
             raise ValueError("images must be floating point (already normalised); use preprocess_u8 for uint8 HWC input")
         return B, H
 
+    @_on_own_device
     def backbone_tokens(self, images: torch.Tensor, *, patches: Optional[torch.Tensor] = None, B=None, S=None):
         """DINOv2 ViT-B/14 `last_hidden_state` [B, 1+N, 768] fp32 (HF modeling_dinov2.py:459-485).
         `patches` (bf16 [B*N, 592] from `preprocess_u8`) may be given instead of images."""
@@ -581,10 +586,38 @@ class CognitiveAimModel(nn.Module):
 
         cont = torch.stack([flat("focal_length", torch.float32), flat("aperture", torch.float32),
                             flat("iso", torch.float32)], dim=1).contiguous()
+        cam_in = exif_data["camera_idx"] if "camera_idx" in exif_data else None
+        if self.validate_inputs and cam_in is not None and not (torch.is_tensor(cam_in) and cam_in.is_cuda):
+            # host-resident indices: checking them costs no synchronisation, so fail at once like nn.Embedding would
+            c = torch.as_tensor(cam_in).reshape(-1)
+            if c.numel() and (int(c.min()) < 0 or int(c.max()) >= self.cfg.num_cameras):
+                raise ValueError("camera_idx out of range")
         cam = flat("camera_idx", torch.int64).contiguous()
-        if self.validate_inputs and (int(cam.min()) < 0 or int(cam.max()) >= self.cfg.num_cameras):
-            raise ValueError("camera_idx out of range")  # (one tiny D2H sync; disable for CUDA-graph capture)
+        # device-resident indices are range-checked inside the heads kernel (no device-to-host sync): _raise_on_fault
         return cont, cam
+
+    def _fault_word(self) -> torch.Tensor:
+        if self._fault is None:
+            self._fault = torch.zeros(1, dtype=torch.int32).pin_memory()
+        return self._fault
+
+    def _raise_on_fault(self, sync: bool = False):
+        """Input faults found by the kernels of EARLIER calls (a camera_idx outside the embedding table: clamped on the
+        device, flagged in a pinned word the host can read without synchronising).  Called at the start of every
+        forward; `check_inputs(sync=True)` waits for the device first, i.e. also covers the call just made."""
+        if self._fault is None:
+            return
+        if sync:
+            torch.cuda.synchronize(self._device())
+        if self.validate_inputs and int(self._fault[0]) != 0:
+            self._fault.zero_()
+            raise ValueError("camera_idx out of range (reported by the device for an earlier forward call; the lookup "
+                             "was clamped into the table)")
+
+    def check_inputs(self, sync: bool = True):
+        """Raise ValueError if any forward so far was given an out-of-range camera_idx (reference: nn.Embedding raises
+        IndexError at src/model.py:491)."""
+        self._raise_on_fault(sync=sync)
 
     def _curiosity_draw(self, B: int):
         """One CuriosityModule run draws randn(B,192) then randn(B,768) on the global CPU generator in eval
@@ -637,8 +670,10 @@ class CognitiveAimModel(nn.Module):
 
     # -- public forward passes --------------------------------------------------------------------------
     @torch.no_grad()
+    @_on_own_device
     def forward_with_guidance(self, images, exif_data=None, attention_guidance=None, return_attention=False):
         """reference src/model.py:1157-1240.  Returns (depth [B,1], confidence [B,1][, attention [B,N]])."""
+        self._raise_on_fault()
         if attention_guidance is None and exif_data is not None and self.use_exif:
             # guidance None -> plain focal-stream features and attention (:1206-1212)
             return self._forward_impl(images, exif_data, return_attention, mode="guided_none")
@@ -684,7 +719,8 @@ class CognitiveAimModel(nn.Module):
             ops.weighted_pool(ws["tokens"], T * _D, 1, ws["heat"], None, ws["pool"], B, N, _D, _POOL_SPLITS)
             ops.heads(pk["heads"], tokens=ws["tokens"], tokens_per_img=T, depth=ws["depth"], conf=ws["conf"], B=B,
                       pool_partial=ws["pool"], pool_splits=_POOL_SPLITS, tmp_w=ws["tmpw"], tmp_b=ws["tmpb"],
-                      pooled_out=ws["pooled"], exif=ws["exif_in"], camera_idx=ws["cam_in"])
+                      pooled_out=ws["pooled"], exif=ws["exif_in"], camera_idx=ws["cam_in"],
+                      num_cameras=self.cfg.num_cameras, fault_ptr=self._fault_word().data_ptr())
             self._curiosity_join()
 
         self._run(ws, ("guided", self._curiosity_key()), device_pass)
@@ -698,6 +734,7 @@ class CognitiveAimModel(nn.Module):
         return (depth, conf, heat) if return_attention else (depth, conf)
 
     @torch.no_grad()
+    @_on_own_device
     def forward(self, images, exif_data=None, return_attention=False):
         """reference src/model.py:1064-1155 (un-guided).  One backbone + one focal pass instead of 3 + 4."""
         return self._forward_impl(images, exif_data, return_attention, mode="forward")
@@ -711,6 +748,7 @@ class CognitiveAimModel(nn.Module):
           guided_none      forward_with_guidance(guidance=None) (:1185, :1206-1212): one run, attention always stored
           guided_fallback  forward_with_guidance without EXIF: the guided attempt (:1185 [+ :1421 projection draws]) fails in
                            `fusion` and falls back to forward() (:1237-1240) with the guided attention already stored."""
+        self._raise_on_fault()
         B, S = self._check_images(images)
         pk = self._pack()
         g = S // 14
@@ -763,7 +801,8 @@ class CognitiveAimModel(nn.Module):
                 ops.guided_softmax(base, ws["mask_in"], ws["heat"], ws["argmax"], B, N)
             ops.heads(pk["heads"], tokens=ws["tokens"], tokens_per_img=T, depth=ws["depth"], conf=ws["conf"], B=B,
                       focal_feat=ws["focal_feat"], exif=ws["exif_in"] if has_exif else None,
-                      camera_idx=ws["cam_in"] if has_exif else None, fused_out=ws["fused"])
+                      camera_idx=ws["cam_in"] if has_exif else None, fused_out=ws["fused"],
+                      num_cameras=self.cfg.num_cameras, fault_ptr=self._fault_word().data_ptr())
             self._curiosity_join()
 
         self._run(ws, ("unguided", has_exif, tuple(roles), mask is not None, self._curiosity_key()), device_pass)
@@ -793,6 +832,7 @@ class CognitiveAimModel(nn.Module):
         return getattr(self, "_last_attention_weights", None)
 
     @torch.no_grad()
+    @_on_own_device
     def get_features_aligned(self, images, exif_data=None):
         """[B, 192] fused features (reference src/model.py:960-1048)."""
         self._forward_impl(images, exif_data, False, mode="features")
@@ -803,6 +843,7 @@ class CognitiveAimModel(nn.Module):
         return self.get_features_aligned(images, exif_data)
 
     @torch.no_grad()
+    @_on_own_device
     def focal_attention(self, tokens: torch.Tensor, want_features: bool = False):
         """IterativeFocalStream on given backbone tokens [B, 1+N, 768] fp32 (test / analysis hook): returns the
         last-iteration attention [B, N] (and the fused 64-d focal features when `want_features`)."""
@@ -819,6 +860,7 @@ class CognitiveAimModel(nn.Module):
         return (att, ws["focal_feat"].clone()) if want_features else att
 
     @torch.no_grad()
+    @_on_own_device
     def focus_map(self, size, attention: Optional[torch.Tensor] = None):
         """The overlay heat map `demo.py:_save_prediction_image` renders (demo.py:530-563): cube, 70th-percentile
         threshold, min-max normalisation, g x g grid, order-1 zoom to `size` = (height, width) of the image it is laid
@@ -840,6 +882,7 @@ class CognitiveAimModel(nn.Module):
 
     # -- demo-style preprocessing ---------------------------------------------------------------------------
     @torch.no_grad()
+    @_on_own_device
     def preprocess(self, images_hwc_u8: torch.Tensor, size: int, mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD):
         """demo.py:162-166 for a batch of same-sized uint8 [B, H, W, 3] images, on the GPU: Resize((size, size)) (Pillow's
         antialiased bilinear resample, bit-exact) -> ToTensor -> Normalize.  Returns float32 [B, 3, size, size], the
@@ -857,6 +900,7 @@ class CognitiveAimModel(nn.Module):
         return x.sub_(m).div_(s).contiguous()                          # Normalize
 
     @torch.no_grad()
+    @_on_own_device
     def preprocess_jpeg(self, jpeg_files, size: int, mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD):
         """demo.py:312-319 for a list of JPEG files given as bytes: decode (nvJPEG) -> Resize((size, size)) (exact Pillow
         arithmetic) -> ToTensor -> Normalize, all on the GPU.  Images may differ in size (each is resized on its own, as
@@ -870,6 +914,7 @@ class CognitiveAimModel(nn.Module):
         return torch.cat(out, dim=0)
 
     @torch.no_grad()
+    @_on_own_device
     def tokens_from_uint8(self, images_hwc_u8: torch.Tensor, size: Optional[int] = None):
         """uint8 [B, H, W, 3] -> backbone tokens: demo.py:162-166 on the GPU — Resize((size, size)) exactly as Pillow does
         it (skipped when the images already have that size or `size` is None), then ToTensor + Normalize + patchify

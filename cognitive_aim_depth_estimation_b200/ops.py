@@ -300,10 +300,13 @@ def make_heads_weights(named):
 
 
 def heads(weights, *, tokens, tokens_per_img, depth, conf, B, focal_feat=None, pool_partial=None, pool_splits=0,
-          tmp_w=None, tmp_b=None, pooled_out=None, exif=None, camera_idx=None, fused_out=None):
+          tmp_w=None, tmp_b=None, pooled_out=None, exif=None, camera_idx=None, fused_out=None, num_cameras=0,
+          fault_ptr=None):
+    """`fault_ptr`: address of a device-visible int32 (pinned host memory) that receives bit 0 when a camera index lies
+    outside [0, num_cameras) — the range check of the embedding lookup, done on the device so the call never syncs."""
     import ctypes as C
     inp = _lib.HeadsInputs(_dp(tokens), tokens_per_img, _dp(focal_feat), _dp(pool_partial), pool_splits, _dp(tmp_w),
-                           _dp(tmp_b), _dp(pooled_out), _dp(exif), _dp(camera_idx))
+                           _dp(tmp_b), _dp(pooled_out), _dp(exif), _dp(camera_idx), int(num_cameras), fault_ptr)
     e0 = _begin()
     check(_lib.load().ca_heads(C.byref(weights), C.byref(inp), ptr(depth), ptr(conf), ptr(fused_out), B, stream_ptr()),
           "ca_heads")

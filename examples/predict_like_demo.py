@@ -77,10 +77,10 @@ def main():
     ap.add_argument("--checkpoint", default=None)
     ap.add_argument("--overlay", default=None, help="write the overlay heat map of the last instruction as .npy")
     args = ap.parse_args()
+    # without a checkpoint: the reference's own random init (demo.py:148-150 "continuing with randomly initialized
+    # weights") — create_model draws it from the global generator exactly like the reference's constructor
     sd = torch.load(args.checkpoint, map_location="cpu") if args.checkpoint else None
-    if sd is None:
-        from oracle import cogaim_oracle as orc  # only to reproduce the reference's random init; not used for compute
-        sd = orc.build_state_dict(0)
+    torch.manual_seed(0)
     p = Predictor(sd, image_size=args.image_size)
     data = open(args.image, "rb").read()
     todo = INSTRUCTIONS if args.instruction == "all" else [args.instruction]

@@ -141,6 +141,8 @@ typedef struct ca_heads_inputs {
   float* pooled_out;          /* optional [B, 768] (debug / tests) */
   const float* exif;          /* [B, 3] raw focal_length, aperture, iso — or NULL (zero EXIF slot) */
   const long long* camera_idx;/* [B] */
+  int num_cameras;            /* rows of cam_emb; an index outside [0, num_cameras) is clamped and reported in *fault */
+  int* fault;                 /* optional device-visible word (e.g. pinned host memory): bit 0 set on a bad camera_idx */
 } ca_heads_inputs;
 
 /* depth[B], conf[B] (and optionally fused_out[B,192]) from the backbone tokens + focal slot + EXIF.

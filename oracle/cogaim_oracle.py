@@ -395,15 +395,27 @@ def ambient_stream(sd: SD, cls: torch.Tensor) -> torch.Tensor:
     return _mlp(sd, cls, ["ambient_stream.mlp.0", "ambient_stream.mlp.3", "ambient_stream.mlp.5"])
 
 
-def curiosity_module(sd: SD, cls: torch.Tensor, update_history: bool = True, prefix: str = "curiosity_module."):
+def _randn_rows(like: torch.Tensor, rng_rows):
+    """`torch.randn_like(like)`, or — when `like` holds only the rows `rows` of a batch of `Bg` images — the same rows
+    of the draw the reference would make for the whole batch (identical generator consumption)."""
+    if rng_rows is None:
+        return torch.randn_like(like)
+    Bg, rows = rng_rows
+    return torch.randn(Bg, like.size(1))[list(rows)]
+
+
+def curiosity_module(sd: SD, cls: torch.Tensor, update_history: bool = True, prefix: str = "curiosity_module.",
+                     rng_rows=None):
     """CuriosityModule.forward (src/model.py:586-688) with exif_data=None, loss_type='robust'.
     Output-dead under the effective config, but it draws randn(B,192) then randn(B,768) from the global
-    CPU generator (:609, :744) and writes the exploration ring buffer (:760-773)."""
+    CPU generator (:609, :744) and writes the exploration ring buffer (:760-773).
+    `rng_rows=(Bg, rows)`: `cls` holds rows `rows` of a batch of `Bg` images (tests of images picked out of a large
+    batch): the noise is drawn at the full batch size, so the generator ends where the reference's would."""
     p = prefix
     mu = _mlp(sd, cls, [p + "encoder_mean.0", p + "encoder_mean.3"])
     logvar = _mlp(sd, cls, [p + "encoder_logvar.0", p + "encoder_logvar.3"])
     std = torch.exp(0.5 * logvar)
-    z = mu + torch.randn_like(std) * std
+    z = mu + _randn_rows(std, rng_rows) * std
     rec = _mlp(sd, z, [p + "decoder.0", p + "decoder.3"])
     diff = rec - cls[:, :rec.size(1)]
     err = torch.sqrt((diff ** 2).sum(dim=1) + 1e-8)
@@ -413,7 +425,7 @@ def curiosity_module(sd: SD, cls: torch.Tensor, update_history: bool = True, pre
     basic = err.clamp(min=0) + 0.1 * kl.clamp(min=0) + 0.1 * unc.clamp(0.0, 10.0)
     geo = torch.full((cls.size(0),), 0.5)  # exif_data is None at every call site (:690-700)
     base = torch.sigmoid(_mlp(sd, cls, [p + "local_curiosity.0", p + "local_curiosity.2"])).squeeze(-1)
-    noisy = cls + torch.randn_like(cls) * 0.01
+    noisy = cls + _randn_rows(cls, rng_rows) * 0.01
     nz = torch.sigmoid(_mlp(sd, noisy, [p + "local_curiosity.0", p + "local_curiosity.2"])).squeeze(-1)
     local = (base + (base - nz).abs() * 0.2).clamp(0.0, 1.0)
     w = torch.softmax(sd[p + "curiosity_weights"], dim=0)
@@ -439,7 +451,7 @@ def heads(sd: SD, feats192: torch.Tensor):
 
 @torch.no_grad()
 def forward_with_guidance(sd: SD, images: torch.Tensor, exif: Optional[dict], guidance, tokens=None,
-                          update_history: bool = True):
+                          update_history: bool = True, rng_rows=None):
     """CognitiveAimModel.forward_with_guidance(..., return_attention=True) (src/model.py:1157-1240) for
     `guidance` a string or tensor and exif given.  Consumes the global CPU RNG exactly like the reference:
     randn(B,192), randn(B,768) (curiosity), then nn.Linear(768,64) init (:1421).
@@ -447,7 +459,7 @@ def forward_with_guidance(sd: SD, images: torch.Tensor, exif: Optional[dict], gu
     if tokens is None:
         tokens = dinov2_tokens(sd, images)
     cls, patches = tokens[:, 0], tokens[:, 1:]
-    score = curiosity_module(sd, cls, update_history)  # :1185 (only consumed when curiosity_guided=True)
+    score = curiosity_module(sd, cls, update_history, rng_rows=rng_rows)  # :1185 (only consumed when curiosity_guided=True)
     amb = ambient_stream(sd, cls)  # :1196
     _, base = iterative_focal_stream(sd, patches, need_features=False,
                                      curiosity_score=score)  # :1257 (features discarded at :1424)

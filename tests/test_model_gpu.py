@@ -201,3 +201,50 @@ def test_lora_merge_target_applies_the_adapters(cuda_device, target):
     moved = ((plain - want).norm() / want.norm()).item()
     assert rel < TOKEN_REL_FRO, rel
     assert moved > 3 * rel, (moved, rel)  # the adapters really changed the tokens
+
+
+def test_camera_idx_range_is_checked_on_the_device(cuda_device, sd, cases):
+    """the default API path must not synchronise.  A camera index outside the embedding table
+    (nn.Embedding would raise, src/model.py:491) is clamped by the heads kernel and flagged in a pinned word: the call
+    itself returns without a device-to-host sync, `check_inputs()` (or the next forward) raises ValueError."""
+    from cognitive_aim_depth_estimation_b200.model import create_model
+    m = create_model(CFG, {"num_cameras": 71}, device=cuda_device)
+    m.load_state_dict(sd)
+    x, ex, _ = cases[(224, 2)]
+    good = _cuda_exif(ex, "cuda")
+    bad = dict(good, camera_idx=torch.tensor([int(ex["camera_idx"][0]), 71], device="cuda"))
+    assert m.validate_inputs
+    torch.manual_seed(11)
+    d0, _ = m.forward_with_guidance(x.cuda(), good, "center")
+    m.check_inputs()                                   # nothing to report
+    torch.manual_seed(11)
+    d1, _ = m.forward_with_guidance(x.cuda(), bad, "center")   # returns: the fault is only flagged
+    assert torch.isfinite(d1).all() and torch.equal(d1[0], d0[0])
+    with pytest.raises(ValueError, match="camera_idx out of range"):
+        m.check_inputs()
+    m.check_inputs()                                   # reported once, then cleared
+    m.forward_with_guidance(x.cuda(), dict(good, camera_idx=torch.tensor([-1, 0], device="cuda")), "center")
+    torch.cuda.synchronize()
+    with pytest.raises(ValueError, match="camera_idx out of range"):
+        m.forward_with_guidance(x.cuda(), good, "center")      # ... or raised by the next call
+    m.validate_inputs = False
+    m.forward_with_guidance(x.cuda(), bad, "center")
+    m.check_inputs()                                   # validation off: clamped silently
+
+
+def test_model_on_a_non_current_device(sd, cases):
+    """every launch must go to the model's own GPU, whatever the caller's current device is."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from cognitive_aim_depth_estimation_b200.model import create_model
+    x, ex, _ = cases[(224, 2)]
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = create_model(CFG, {"num_cameras": 71}, device=dev)
+        m.load_state_dict(sd)
+        torch.cuda.set_device(0)                       # current device stays 0 for both models
+        torch.manual_seed(11)
+        outs.append([t.cpu() for t in m.forward_with_guidance(x.to(dev), _cuda_exif(ex, dev), "left",
+                                                               return_attention=True)])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
