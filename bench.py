@@ -134,6 +134,124 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------
+# The other BASELINE.json configurations, measured after the headline region on the same box (N = 1 only)
+# ------------------------------------------------------------------------------------------------------
+def _timed_region(fn, dev_index: int, target_s: float = 0.8):
+    """warm-up (3 calls, the first captures the CUDA graph), then K calls timed with CUDA events on the launching stream,
+    K chosen so the region lasts ~target_s (at least two 200 ms clock samples).  -> (ms per call, K, clocks)"""
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn(3)
+    e1.record()
+    torch.cuda.synchronize()
+    k = int(min(80, max(6, target_s * 1e3 / max(e0.elapsed_time(e1), 1e-3) + 1)))
+    sampler = ClockSampler(dev_index)
+    sampler.start()
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(k):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / k, k, sampler.stop()
+
+
+def other_configs(model, dev, local_rank: int, ex_fn, img_fn):
+    """configs[2] (backbone only), configs[3]'s per-GPU shape (64 images), configs[4] (1036 x 1036), the un-guided
+    `forward`, and the demo-shaped uint8 flow end to end — each its own timed region with its own clock record.
+    Inputs are device-resident (three rotating batches, larger than L2 together with the activations) except for the
+    uint8 flow, which is timed on the wall clock with the H2D / D2H copies inside."""
+    out = {}
+
+    def entry(name, workload, B, S_, ms, k, clocks, gflop_per_image=None, **extra):
+        d = {"workload": workload, "batch_per_gpu": B, "image_size": S_, "ms_per_step": ms, "steps": k,
+             "value": B / (ms / 1e3), "unit": "images/s", "clocks": clocks}
+        if gflop_per_image:
+            d["whole_step_tflops"] = gflop_per_image * d["value"] / 1e3
+        d.update(extra)
+        out[name] = d
+
+    # configs[2]: backbone only, 518 x 518, 32 images
+    B, S_ = 32, 518
+    imgs = [img_fn(B, S_, 100 + i).to(dev) for i in range(3)]
+    ms, k, ck = _timed_region(lambda i: model.backbone_tokens(imgs[i % 3]), local_rank)
+    entry("configs[2] backbone only", "Dinov2Model last_hidden_state (eval_configs/baseline_dinov2_config.yaml)", B, S_, ms,
+          k, ck, ALGO_GFLOP_BACKBONE[518])
+    # un-guided forward (src/model.py:1064), same inputs
+    ex = {kk: v.to(dev) for kk, v in ex_fn(B, 300).items()}
+    ms, k, ck = _timed_region(lambda i: model(imgs[i % 3], ex, return_attention=True), local_rank)
+    entry("un-guided forward", "CognitiveAimModel.forward(images, exif, return_attention=True)", B, S_, ms, k, ck)
+    # demo-shaped flow end to end: pinned uint8 HWC on the host -> H2D (25.8 MB / step) -> fused normalise + patchify ->
+    # guided forward -> depth / confidence / heat-map back to pinned host memory; wall clock
+    g = torch.Generator().manual_seed(1235)
+    host_u8 = [torch.randint(0, 256, (B, S_, S_, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(3)]
+    stage = [torch.empty(B, S_, S_, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
+    outs = [torch.empty(B, 1).pin_memory(), torch.empty(B, 1).pin_memory(), torch.empty(B, (S_ // 14) ** 2).pin_memory()]
+    copy_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def u8_loop(n):
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        with torch.cuda.stream(copy_stream):
+            stage[0].copy_(host_u8[0], non_blocking=True)
+            ready[0].record()
+        for i in range(n):
+            cur = i % 2
+            torch.cuda.current_stream().wait_event(ready[cur])
+            if i + 1 < n:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(done[1 - cur])
+                    stage[1 - cur].copy_(host_u8[(i + 1) % 3], non_blocking=True)
+                    ready[1 - cur].record()
+            torch.manual_seed(11)
+            res = model.forward_with_guidance(stage[cur], ex, INSTRUCTIONS[i % 9], return_attention=True)
+            done[cur].record()
+            d2h_stream.wait_event(done[cur])
+            with torch.cuda.stream(d2h_stream):
+                for dst, src in zip(outs, res):
+                    dst.copy_(src, non_blocking=True)
+                    src.record_stream(d2h_stream)
+        torch.cuda.synchronize()
+
+    u8_loop(4)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n = 40
+    t0 = time.perf_counter()
+    u8_loop(n)
+    wall = time.perf_counter() - t0
+    entry("uint8 end to end", "pinned uint8 [B,518,518,3] on the host -> H2D -> normalise+patchify -> guided forward -> "
+          "outputs D2H (demo.py:312-346 flow), wall clock", B, S_, wall / n * 1e3, n, sampler.stop(),
+          h2d_bytes_per_step=B * S_ * S_ * 3 + 64 * 768 * 4 + 64 * 4, d2h_bytes_per_step=B * (2 + (S_ // 14) ** 2) * 4)
+    del imgs, host_u8, stage
+    # configs[3]'s per-GPU shape: 64 images per call
+    B = 64
+    imgs = [img_fn(B, S_, 200 + i).to(dev) for i in range(3)]
+    ex = {kk: v.to(dev) for kk, v in ex_fn(B, 301).items()}
+
+    def guided(i):
+        torch.manual_seed(11)
+        return model.forward_with_guidance(imgs[i % 3], ex, INSTRUCTIONS[i % 9], return_attention=True)
+
+    ms, k, ck = _timed_region(guided, local_rank)
+    entry("configs[3] per-GPU shape", "full cognitive model + EXIF, guided forward, 64 images per call", B, S_, ms, k, ck,
+          ALGO_GFLOP_BY_SIZE[518])
+    del imgs
+    # configs[4]: 1036 x 1036 (4x tokens), 8 images per call
+    B, S_ = 8, 1036
+    imgs = [img_fn(B, S_, 400 + i).to(dev) for i in range(3)]
+    ex = {kk: v.to(dev) for kk, v in ex_fn(B, 302).items()}
+    ms, k, ck = _timed_region(guided, local_rank)
+    entry("configs[4] 1036x1036", "full cognitive model, guided forward, 5477 tokens per image", B, S_, ms, k, ck,
+          ALGO_GFLOP_BY_SIZE[1036])
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
 # Candidate arm
 # ------------------------------------------------------------------------------------------------------
 def run_candidate(args):
@@ -316,6 +434,11 @@ def run_candidate(args):
         "kernel_breakdown_note": "second pass of the same steps launched eagerly with per-launch CUDA events; `value` is "
                                  "the CUDA-graph replay of the same launch sequence (use_cuda_graphs=%s)" % model.use_cuda_graphs,
     }
+    if world == 1 and not args.no_other_configs and not backbone_only and B == BATCH_PER_GPU and S == 518:
+        del dev_imgs, stage
+        torch.cuda.empty_cache()
+        line["other_configs"] = other_configs(model, dev, local_rank, lambda b, seed: orc.synthetic_exif(b, seed=seed),
+                                              lambda b, s_, seed: orc.synthetic_images(b, s_, seed=seed))
     if world == 1 and not args.no_cpu_baseline and not backbone_only:
         r = cpu_reference(steps=3, warmup=1, images_per_step=2)
         line["cpu_baseline"] = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port",
@@ -334,6 +457,8 @@ def main():
     ap.add_argument("--impl", default="candidate", choices=["candidate", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the extra timed regions (configs[2..4], un-guided forward, uint8 end to end) after the headline")
     ap.add_argument("--image-size", type=int, default=518, choices=sorted(ALGO_GFLOP_BY_SIZE),
                     help="sweep configs of BASELINE.json (224 / 1036); the headline metric is quoted at 518")
     ap.add_argument("--workload", default="guided", choices=["guided", "backbone"],

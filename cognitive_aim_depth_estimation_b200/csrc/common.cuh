@@ -163,6 +163,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking test: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // try_wait with a suspend-time hint: the hardware may keep the thread parked (no issue slots spent) for up to `ns`
 // before reporting failure, and wakes it as soon as the phase completes.  For the control warps (TMA producer, MMA
 // issuer) that share a scheduler with compute warps, a plain try_wait loop returns after a short default window and

@@ -177,6 +177,7 @@ class CognitiveAimModel(nn.Module):
         self._packed_key = None
         self._tables: Dict = {}   # per-grid tables (pos-embed, PE, centre bias, masks)
         self._ws: Dict = {}       # workspaces keyed by (B, S)
+        self.input_size = None        # side uint8 [B, H, W, 3] inputs are resized to (demo.py's dataset.image_size); None = as given
         self.validate_inputs = True   # camera_idx range faults (checked on the device) are raised at the next call
         self._fault = None            # pinned int32 the heads kernel flags input faults in
         self.rng_replay_batch = None  # sharded runs: replay the reference's RNG draws at the GLOBAL batch size
@@ -451,16 +452,39 @@ class CognitiveAimModel(nn.Module):
         ops.fetch_pinned(ws["cur_eps"][:k], bufs[0][:k])
         ops.fetch_pinned(ws["cur_noise"][:k], bufs[1][:k])
 
-    @staticmethod
-    def _check_images(images):
+    def _check_images(self, images):
+        """(B, S) of a forward input: float [B, 3, S, S] already normalised (what the reference's forward takes), or —
+        an extension for the demo-shaped flow — uint8 [B, H, W, 3] straight from the decoder (demo.py:312-319 on the
+        GPU: Resize((input_size, input_size)) when the size differs, ToTensor, Normalize, fused with the patchify)."""
+        if torch.is_tensor(images) and images.dtype == torch.uint8:
+            if images.dim() != 4 or images.shape[-1] != 3:
+                raise ValueError("uint8 images must be [B, H, W, 3]")
+            B, H, W, _ = images.shape
+            S = self.input_size if self.input_size is not None else H
+            if self.input_size is None and H != W:
+                raise ValueError("uint8 images must be square, or set model.input_size to resize like demo.py")
+            if S < 56 or S % 14 != 0:
+                raise ValueError(f"image side must be a multiple of 14 and >= 56 (got {S})")
+            return B, S
         if not torch.is_tensor(images) or images.dim() != 4 or images.shape[1] != 3:
             raise ValueError("images must be a [B, 3, S, S] tensor")
         B, _, H, W = images.shape
         if H != W or H < 56:
             raise ValueError(f"images must be square with side >= 56 (got {H} x {W})")
         if not images.is_floating_point():
-            raise ValueError("images must be floating point (already normalised); use preprocess_u8 for uint8 HWC input")
+            raise ValueError("images must be floating point (already normalised) or uint8 [B, H, W, 3]")
         return B, H
+
+    def _patch_rows(self, images, ws, S: int):
+        """im2col rows (bf16 [B*N, 592]) of the batch into ws['patches']; returns (patches, tensor to keep alive)."""
+        dev = self._device()
+        if images.dtype == torch.uint8:
+            u8 = images.to(dev).contiguous()
+            if tuple(u8.shape[1:3]) != (S, S):
+                u8 = ops.resize_u8(u8, S, S)  # demo.py:162-163: Pillow's antialiased bilinear resample, bit-exact
+            return ops.preprocess_u8(u8, ws["patches"]), u8
+        x = images.to(dev, torch.float32).contiguous()
+        return ops.patchify_f32(x, ws["patches"]), x
 
     @_on_own_device
     def backbone_tokens(self, images: torch.Tensor, *, patches: Optional[torch.Tensor] = None, B=None, S=None):
@@ -470,13 +494,12 @@ class CognitiveAimModel(nn.Module):
         dev = self._device()
         if patches is None:
             B, S = self._check_images(images)
-            images = images.to(dev, torch.float32).contiguous()
         g = S // 14
         N, T = g * g, g * g + 1
         ws = self._workspace(B, S)
         tb = self._grid_tables(g)
         if patches is None:
-            patches = ops.patchify_f32(images, ws["patches"])
+            patches, images = self._patch_rows(images, ws, S)
         self._run(ws, ("backbone", patches.data_ptr()), lambda: self._backbone_layers(ws, patches, B, S))
         return ws["tokens"]
 
@@ -706,9 +729,8 @@ class CognitiveAimModel(nn.Module):
         slot["event"].record()
         ws["exif_in"].copy_(exif, non_blocking=True)
         ws["cam_in"].copy_(cam, non_blocking=True)
-        images = images.to(dev, torch.float32).contiguous()
         self._grid_tables(g)
-        patches = ops.patchify_f32(images, ws["patches"])
+        patches, images = self._patch_rows(images, ws, S)
         cur_weight = ws["cur_weight"][0] if self.cfg.curiosity_guided else None
 
         def device_pass():
@@ -780,9 +802,8 @@ class CognitiveAimModel(nn.Module):
             ws["cam_in"].copy_(cam, non_blocking=True)
         if mask is not None:
             ws["mask_in"].copy_(mask, non_blocking=True)
-        images = images.to(self._device(), torch.float32).contiguous()
         self._grid_tables(g)
-        patches = ops.patchify_f32(images, ws["patches"])
+        patches, images = self._patch_rows(images, ws, S)
         cg = self.cfg.curiosity_guided
         jf = roles.index("features")
 

@@ -3,7 +3,7 @@
 # Usage (from the repo root, under gpurun):  bash profiles/run_ncu.sh <tag>
 set -u
 TAG=${1:-r01}
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --batch 32"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs --batch 32"
 mkdir -p gpurun_out
 if [ -z "${FULL_ONLY:-}" ]; then
 $CMD > gpurun_out/plain_${TAG}.log 2>&1 &&

@@ -248,3 +248,27 @@ def test_model_on_a_non_current_device(sd, cases):
                                                                return_attention=True)])
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def test_uint8_images_through_the_forward(model, cases):
+    """demo-shaped flow: uint8 [B, H, W, 3] straight into forward_with_guidance / forward (Resize when `input_size` is
+    set, ToTensor, Normalize fused with the patchify) == the float path on model.preprocess() of the same images."""
+    u8 = torch.randint(0, 256, (2, 300, 400, 3), generator=torch.Generator().manual_seed(5), dtype=torch.uint8).cuda()
+    _, ex, _ = cases[(224, 2)]
+    exg = _cuda_exif(ex, "cuda")
+    model.input_size = 224
+    try:
+        torch.manual_seed(11)
+        a = [t.clone() for t in model.forward_with_guidance(u8, exg, "right", return_attention=True)]
+        ua = [t.clone() for t in model(u8, exg, return_attention=True)]
+    finally:
+        model.input_size = None
+    xf = model.preprocess(u8, 224)
+    torch.manual_seed(11)
+    b = model.forward_with_guidance(xf, exg, "right", return_attention=True)
+    ub = model(xf, exg, return_attention=True)
+    for p, q in list(zip(a, b)) + list(zip(ua, ub)):
+        assert (p - q).abs().max().item() <= 2e-3 * max(1.0, q.abs().max().item())
+    assert torch.equal(a[2].argmax(-1), b[2].argmax(-1))
+    with pytest.raises(ValueError):
+        model.forward_with_guidance(u8, exg, "right")          # not square and no input_size

@@ -2,7 +2,7 @@
 # same-box A/B of two checkouts of the repo: tools/ab_bench.sh <dirA> <dirB> [bench args]
 A=$1; B=$2; shift 2
 for r in 1 2 3; do for d in $A $B; do
-  python $d/bench.py --steps 18 --warmup 4 --no-cpu-baseline "$@" > /tmp/ab.json 2>/dev/null
+  python $d/bench.py --steps 18 --warmup 4 --no-cpu-baseline --no-other-configs "$@" > /tmp/ab.json 2>/dev/null
   python - <<PY
 import json
 d=json.load(open("/tmp/ab.json"))
