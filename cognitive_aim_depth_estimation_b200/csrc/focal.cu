@@ -45,9 +45,11 @@ __global__ void rowstats_merge_kernel(const float* __restrict__ pm, const float*
     for (int i = 0; i < P; ++i) wtab[static_cast<size_t>(r) * P + i] = exp2f(m[i] - mx) * ri;
 }
 
-// Column sums of the (weighted) row softmax from the stored exponentials: pc[b, j, p] = sum over the 64 rows i of row
+// Column sums of the (weighted) row softmax from the stored exponentials: pc[b, p, j] = sum over the 64 rows i of row
 // span p of E[b, i, j] * wtab[b, i, j / 64].  One thread = 8 consecutive columns (one 16-byte fp16 load per row);
-// grid = (column chunks, row spans, images).  Bandwidth-bound: reads E once (2 bytes per score).
+// grid = (column chunks, row spans, images).  Bandwidth-bound: reads E once (2 bytes per score).  The partials are
+// span-major ([B, P, N]): a CTA's results are one contiguous row (the column-major form, 4-byte stores 4 P bytes apart,
+// cost this kernel half its time in partial-sector writes: 0.38 -> see profiles/README.md of the HBM rate).
 __global__ void __launch_bounds__(192) colsum_e_kernel(const __half* __restrict__ E, int lde, long long e_batch_stride,
                                                         const float* __restrict__ wtab, float* __restrict__ pc, int N,
                                                         int P) {
@@ -61,26 +63,38 @@ __global__ void __launch_bounds__(192) colsum_e_kernel(const __half* __restrict_
   const __half* e = E + static_cast<size_t>(b) * e_batch_stride + static_cast<size_t>(i0) * lde + j0;
   const float* w = wtab + (static_cast<size_t>(b) * N + i0) * P + span;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-  for (int i = i0; i < i1; ++i) {
-    const uint4 q = *reinterpret_cast<const uint4*>(e);
-    const float wi = __ldg(w);
-    const __half2* h = reinterpret_cast<const __half2*>(&q);
+  // 16 rows per batch, ALL loads of a batch issued before the first use: 16 x 512 B in flight per warp.  (Written as one
+  // load-use loop the compiler kept two loads in flight per thread and the kernel sat at 0.38 of the HBM rate.)
+  constexpr int kBatch = 16;
+  for (int i = i0; i < i1; i += kBatch) {
+    uint4 q[kBatch];
+    float wi[kBatch];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 f = __half22float2(h[t]);
-      acc[2 * t + 0] = fmaf(f.x, wi, acc[2 * t + 0]);
-      acc[2 * t + 1] = fmaf(f.y, wi, acc[2 * t + 1]);
+    for (int u = 0; u < kBatch; ++u) {
+      const bool in = i + u < i1;
+      q[u] = in ? __ldg(reinterpret_cast<const uint4*>(e + static_cast<size_t>(u) * lde)) : make_uint4(0u, 0u, 0u, 0u);
+      wi[u] = in ? __ldg(w + u * P) : 0.f;
     }
-    e += lde;
-    w += P;
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const __half2* h = reinterpret_cast<const __half2*>(&q[u]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(h[t]);
+        acc[2 * t + 0] = fmaf(f.x, wi[u], acc[2 * t + 0]);
+        acc[2 * t + 1] = fmaf(f.y, wi[u], acc[2 * t + 1]);
+      }
+    }
+    e += static_cast<size_t>(kBatch) * lde;
+    w += kBatch * P;
   }
+  float* out = pc + (static_cast<size_t>(b) * P + p) * N + j0;
 #pragma unroll
   for (int t = 0; t < 8; ++t)
-    if (j0 + t < N) pc[(static_cast<size_t>(b) * N + j0 + t) * P + p] = acc[t];
+    if (j0 + t < N) out[t] = acc[t];
 }
 
-// One CTA per image.  pc: [B, N, P] column-sum partials.  attn[b, j] = final_attention of the iteration.
+// One CTA per image.  pc: [B, P, N] column-sum partials (span-major, as ca_colsum_e writes them).  attn[b, j] = final_attention of the iteration.
 // rowscale_out[b, j] = rowscale_in[b, j] * (1 + focus_strength * attn)  when rowscale_out != nullptr.
 // mode 0: FocalStream attention  (mean over rows, centre bias, L1, clamp, renorm)   src/model.py:234-282
 // mode 1: plain sum of partials (weighted column sums for the un-guided value path; no bias / normalisation)
@@ -93,14 +107,13 @@ __global__ void __launch_bounds__(256) focal_finalize_kernel(const float* __rest
                                                               float adaptive_weight) {
   __shared__ float red[32];
   const int b = blockIdx.x;
-  const float* pcb = pc + static_cast<size_t>(b) * N * P;
+  const float* pcb = pc + static_cast<size_t>(b) * P * N;
   float* ab = attn + static_cast<size_t>(b) * N;
   const float invN = 1.0f / static_cast<float>(N);
   float local = 0.f;
   for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    const float* p = pcb + static_cast<size_t>(j) * P;
     float s = 0.f;
-    for (int i = 0; i < P; ++i) s += p[i];
+    for (int i = 0; i < P; ++i) s += pcb[static_cast<size_t>(i) * N + j];
     const float v = (mode == 0) ? (s * invN + cbias[j]) : s;
     ab[j] = v;
     local += v;
@@ -202,15 +215,23 @@ __global__ void __launch_bounds__(192) weighted_pool_kernel(const float* __restr
   const float* w2b = w2 ? w2 + static_cast<size_t>(b) * N : nullptr;
   const int dv = D / 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-  for (int n = n0; n < n1; ++n) {
-    float g = wb[n];
-    if (w2b) g *= w2b[n];
-    const float4 t = s4[static_cast<size_t>(n) * dv + threadIdx.x];
-    acc.x = fmaf(g, t.x, acc.x);
-    acc.y = fmaf(g, t.y, acc.y);
-    acc.z = fmaf(g, t.z, acc.z);
-    acc.w = fmaf(g, t.w, acc.w);
+  constexpr int kBatch = 8;  // loads of a batch issued together (memory-level parallelism), then the FMAs in row order
+  for (int n = n0; n < n1; n += kBatch) {
+    float4 t[kBatch];
+    float g[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const bool in = n + u < n1;
+      t[u] = in ? s4[static_cast<size_t>(n + u) * dv + threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+      g[u] = in ? (w2b ? wb[n + u] * w2b[n + u] : wb[n + u]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      acc.x = fmaf(g[u], t[u].x, acc.x);
+      acc.y = fmaf(g[u], t[u].y, acc.y);
+      acc.z = fmaf(g[u], t[u].z, acc.z);
+      acc.w = fmaf(g[u], t[u].w, acc.w);
+    }
   }
   reinterpret_cast<float4*>(partial + (static_cast<size_t>(b) * gridDim.x + split) * D)[threadIdx.x] = acc;
 }

@@ -12,68 +12,87 @@ constexpr int kPatchK = 3 * kPatch * kPatch;  // 588
 constexpr int kPatchKPad = 592;               // row stride of the patch matrix: 16-byte multiple for TMA
 
 // ---------------------------------------------------------------------------------------------
-// K1b: fp32 CHW image (already normalised; what `forward` receives) -> bf16 patch rows
-//      row (b, py, px), column k = c*196 + ky*14 + kx   (Conv2d weight.flatten(1) order, HF modeling_dinov2.py:139-148)
-// One warp per (patch row py, channel c, ky): it reads a contiguous image row segment of g*14 floats (coalesced) and
-// scatters 14-element pieces to the g patch rows.
+// K1: image -> bf16 patch rows (im2col of the 14 x 14 / stride 14 patch embedding, HF modeling_dinov2.py:139-148)
+//      row (b, py, px), column k = c*196 + ky*14 + kx  (Conv2d weight.flatten(1) order), columns 588..591 zero
+//   kU8 = false: fp32 CHW, already normalised (what `forward` receives)
+//   kU8 = true : uint8 HWC at model resolution -> ToTensor (/255) -> Normalize(mean, std)  (demo.py:162-166)
+// One CTA per (image, patch row py).  Phase 1 stages the 14 image lines of that patch row in shared memory with fully
+// coalesced reads (for HWC uint8 they are ONE contiguous region of 14*S*3 bytes, read 16 bytes per thread); phase 2
+// writes the g patch rows whole — 1184 contiguous bytes each, 4-byte stores, consecutive lanes on consecutive words.
+// (The first version scattered 28-byte pieces from one warp per image line: 0.16 / 0.49 of the HBM rate,
+// profiles/README.md round 2.)
 // ---------------------------------------------------------------------------------------------
-__global__ void patchify_f32_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ patches, int B, int S,
-                                    int g) {
-  const int line = blockIdx.x * (blockDim.x >> 5) + warp_id();  // over B*3*g*14 image lines that matter
-  const int lines = B * 3 * g * kPatch;
-  if (line >= lines) return;
-  const int ky = line % kPatch;
-  int t = line / kPatch;
-  const int py = t % g;
-  t /= g;
-  const int c = t % 3;
-  const int b = t / 3;
-  const float* src = img + ((static_cast<size_t>(b) * 3 + c) * S + (py * kPatch + ky)) * S;
-  __nv_bfloat16* dst = patches + (static_cast<size_t>(b) * g * g + static_cast<size_t>(py) * g) * kPatchKPad +
-                       c * (kPatch * kPatch) + ky * kPatch;
+template <bool kU8>
+__global__ void __launch_bounds__(320) patch_rows_kernel(const void* __restrict__ img_v,
+                                                          __nv_bfloat16* __restrict__ patches, int S, int g, float3 mean,
+                                                          float3 inv_std) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int py = blockIdx.x;
+  const int b = blockIdx.y;
   const int w = g * kPatch;
-  for (int x = lane_id(); x < w; x += 32) {
-    const int px = x / kPatch;
-    const int kx = x - px * kPatch;
-    dst[static_cast<size_t>(px) * kPatchKPad + kx] = __float2bfloat16_rn(__ldg(src + x));
+  int head = 0;
+  if constexpr (kU8) {
+    const uint8_t* src = static_cast<const uint8_t*>(img_v) + (static_cast<size_t>(b) * S + py * kPatch) * S * 3;
+    const int len = kPatch * S * 3;
+    head = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
+    const uint4* s4 = reinterpret_cast<const uint4*>(src - head);  // aligned down: stays inside the allocation
+    const int n_full = (head + len) / 16;                          // 16-byte words that end inside the region
+    for (int i = threadIdx.x; i < n_full; i += blockDim.x) reinterpret_cast<uint4*>(sm)[i] = __ldg(s4 + i);
+    for (int i = n_full * 16 + threadIdx.x; i < head + len; i += blockDim.x) sm[i] = __ldg(src - head + i);
+  } else {
+    const float* img = static_cast<const float*>(img_v);
+    __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(sm);  // [3 * 14][w]
+    for (int line = warp_id(); line < 3 * kPatch; line += (blockDim.x >> 5)) {
+      const int c = line / kPatch;
+      const int ky = line - c * kPatch;
+      const float* src = img + ((static_cast<size_t>(b) * 3 + c) * S + (py * kPatch + ky)) * S;
+      for (int x = lane_id(); x < w; x += 32) t[line * w + x] = __float2bfloat16_rn(__ldg(src + x));
+    }
   }
-}
-
-// zero the 4 pad columns (588..591) of every patch row once per call
-__global__ void patch_pad_kernel(__nv_bfloat16* __restrict__ patches, int rows) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < rows) {
-    uint2 z = make_uint2(0u, 0u);
-    *reinterpret_cast<uint2*>(patches + static_cast<size_t>(r) * kPatchKPad + kPatchK) = z;
+  __syncthreads();
+  // Phase 2: thread kp owns the bf16x2 word kp (columns 2kp, 2kp+1) of EVERY patch row of this CTA: the column -> (c, ky, kx)
+  // decode happens once per thread, the loop over the g patches only steps the source by one patch width, and the
+  // stores of a warp are 32 consecutive words of one patch row.
+  constexpr int kPairs = kPatchKPad / 2;  // 296 bf16x2 words per patch row
+  const int kp = threadIdx.x;
+  if (kp >= kPairs) return;
+  int off[2];
+  bool ok[2];
+  int ch[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = 2 * kp + e;
+    ok[e] = k < kPatchK;
+    const int c = ok[e] ? k / (kPatch * kPatch) : 0;
+    const int r = ok[e] ? k - c * (kPatch * kPatch) : 0;
+    const int ky = r / kPatch;
+    const int kx = r - ky * kPatch;
+    ch[e] = c;
+    off[e] = kU8 ? head + (ky * S + kx) * 3 + c : (c * kPatch + ky) * w + kx;
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1a: uint8 HWC image at model resolution -> ToTensor (/255) -> Normalize(mean,std) -> bf16 patch rows
-//      (demo.py:162-166 with a source already S x S, so Resize is the identity)
-// One warp per (b, image row y): reads 3*S contiguous bytes, writes pieces of 14 to each patch row.
-// ---------------------------------------------------------------------------------------------
-__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ patches, int B, int S,
-                                     int g, float3 mean, float3 inv_std) {
-  const int line = blockIdx.x * (blockDim.x >> 5) + warp_id();
-  const int lines = B * g * kPatch;
-  if (line >= lines) return;
-  const int y = line % (g * kPatch);
-  const int b = line / (g * kPatch);
-  const int py = y / kPatch;
-  const int ky = y - py * kPatch;
-  const uint8_t* src = img + (static_cast<size_t>(b) * S + y) * S * 3;
-  __nv_bfloat16* dst = patches + (static_cast<size_t>(b) * g * g + static_cast<size_t>(py) * g) * kPatchKPad + ky * kPatch;
-  const int w = g * kPatch * 3;
-  for (int i = lane_id(); i < w; i += 32) {
-    const int x = i / 3;
-    const int c = i - x * 3;
-    const int px = x / kPatch;
-    const int kx = x - px * kPatch;
-    const float m = c == 0 ? mean.x : (c == 1 ? mean.y : mean.z);
-    const float s = c == 0 ? inv_std.x : (c == 1 ? inv_std.y : inv_std.z);
-    const float v = (static_cast<float>(src[i]) / 255.0f - m) * s;
-    dst[static_cast<size_t>(px) * kPatchKPad + c * (kPatch * kPatch) + kx] = __float2bfloat16_rn(v);
+  uint32_t* out = reinterpret_cast<uint32_t*>(patches + (static_cast<size_t>(b) * g * g + static_cast<size_t>(py) * g) * kPatchKPad) + kp;
+  const int step = kU8 ? kPatch * 3 : kPatch;
+  if constexpr (kU8) {
+    // (v / 255 - mean) / std as one table look-up per channel and byte value would need 1.5 KB of smem; the arithmetic is
+    // 3 instructions per element, cheaper than the second shared-memory access
+    const float m0 = ch[0] == 0 ? mean.x : (ch[0] == 1 ? mean.y : mean.z);
+    const float m1 = ch[1] == 0 ? mean.x : (ch[1] == 1 ? mean.y : mean.z);
+    const float s0 = ch[0] == 0 ? inv_std.x : (ch[0] == 1 ? inv_std.y : inv_std.z);
+    const float s1 = ch[1] == 0 ? inv_std.x : (ch[1] == 1 ? inv_std.y : inv_std.z);
+#pragma unroll 4
+    for (int px = 0; px < g; ++px) {
+      const float a = ok[0] ? (static_cast<float>(sm[off[0] + px * step]) / 255.0f - m0) * s0 : 0.f;
+      const float c = ok[1] ? (static_cast<float>(sm[off[1] + px * step]) / 255.0f - m1) * s1 : 0.f;
+      out[static_cast<size_t>(px) * kPairs] = pack_bf16x2(a, c);
+    }
+  } else {
+    const uint16_t* t = reinterpret_cast<const uint16_t*>(sm);
+#pragma unroll 4
+    for (int px = 0; px < g; ++px) {
+      const uint32_t a = ok[0] ? t[off[0] + px * step] : 0u;
+      const uint32_t c = ok[1] ? t[off[1] + px * step] : 0u;
+      out[static_cast<size_t>(px) * kPairs] = a | (c << 16);
+    }
   }
 }
 
@@ -165,31 +184,34 @@ __global__ void __launch_bounds__(256) focal_input_kernel(const float* __restric
 
 }  // namespace
 
+template <bool kU8>
+static int patch_rows_launch(const void* images, __nv_bfloat16* patches, int B, int S, float3 mean, float3 inv_std,
+                             cudaStream_t stream) {
+  const int g = S / kPatch;
+  const size_t smem = kU8 ? static_cast<size_t>(kPatch) * S * 3 + 32 : static_cast<size_t>(3) * kPatch * g * kPatch * 2;
+  CA_REQUIRE(smem <= 200 * 1024, "patchify: image side too large for the shared-memory staging (max ~2400)");
+  static PerDeviceOnce configured;  // per instantiation and per device
+  CA_TRY(configured.run([&]() -> int {
+    CA_CUDA(cudaFuncSetAttribute(patch_rows_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return 0;
+  }));
+  patch_rows_kernel<kU8><<<dim3(g, B), 320, smem, stream>>>(images, patches, S, g, mean, inv_std);
+  CA_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int patchify_f32_launch(const float* images, __nv_bfloat16* patches, int B, int S, cudaStream_t stream) {
   CA_REQUIRE(images && patches, "patchify: null pointer");
   CA_REQUIRE(B > 0 && S >= kPatch, "patchify: bad shape");
-  const int g = S / kPatch;
-  const int rows = B * g * g;
-  patch_pad_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(patches, rows);
-  const int lines = B * 3 * g * kPatch;
-  patchify_f32_kernel<<<(lines + 7) / 8, 256, 0, stream>>>(images, patches, B, S, g);
-  CA_CUDA(cudaGetLastError());
-  return 0;
+  return patch_rows_launch<false>(images, patches, B, S, make_float3(0.f, 0.f, 0.f), make_float3(1.f, 1.f, 1.f), stream);
 }
 
 int preprocess_u8_launch(const uint8_t* images, __nv_bfloat16* patches, int B, int S, const float* mean3,
                          const float* std3, cudaStream_t stream) {
   CA_REQUIRE(images && patches && mean3 && std3, "preprocess: null pointer");
   CA_REQUIRE(B > 0 && S >= kPatch, "preprocess: bad shape");
-  const int g = S / kPatch;
-  const int rows = B * g * g;
-  patch_pad_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(patches, rows);
-  const int lines = B * g * kPatch;
-  preprocess_u8_kernel<<<(lines + 7) / 8, 256, 0, stream>>>(
-      images, patches, B, S, g, make_float3(mean3[0], mean3[1], mean3[2]),
-      make_float3(1.0f / std3[0], 1.0f / std3[1], 1.0f / std3[2]));
-  CA_CUDA(cudaGetLastError());
-  return 0;
+  return patch_rows_launch<true>(images, patches, B, S, make_float3(mean3[0], mean3[1], mean3[2]),
+                                 make_float3(1.0f / std3[0], 1.0f / std3[1], 1.0f / std3[2]), stream);
 }
 
 // dst[i] = src[i], src in PINNED HOST memory read by the SMs over PCIe (UVA).  For the few hundred KB of per-call inputs

@@ -382,7 +382,7 @@ class CognitiveAimModel(nn.Module):
                 "qkv": torch.empty(B * T, 3 * _D, **bf), "att": torch.empty(B * T, _D, **bf),
                 "mlp": torch.empty(B * T, _MLP, **bf), "tokens": torch.empty(B, T, _D, **fl),
                 "xin": torch.empty(B * N, _D, **bf), "qk": torch.empty(B * N, 2 * _D, **bf),
-                "pm": torch.empty(B, N, P, **fl), "ps": torch.empty(B, N, P, **fl), "pc": torch.empty(B, N, P, **fl),
+                "pm": torch.empty(B, N, P, **fl), "ps": torch.empty(B, N, P, **fl), "pc": torch.empty(B, P, N, **fl),
                 "rmax": torch.empty(B, N, **fl), "rinv": torch.empty(B, N, **fl),
                 # span-relative exponentials of the focal scores (fp16) + the per-(row, span) factors that turn them into
                 # softmax probabilities: the column sums are a bandwidth pass over E instead of a second Q K^T

@@ -132,7 +132,7 @@ def patchify_f32(images, patches):
     B, _, S, _ = images.shape
     e0 = _begin()
     check(_lib.load().ca_patchify_f32(ptr(images), ptr(patches), B, S, stream_ptr()), "ca_patchify_f32")
-    _end(e0, "patchify", 2, float(images.numel() * 4 + patches.numel() * 2))
+    _end(e0, "patchify", 1, float(images.numel() * 4 + patches.numel() * 2))
     return patches
 
 
@@ -145,7 +145,7 @@ def preprocess_u8(images_hwc, patches, mean=IMAGENET_MEAN, std=IMAGENET_STD):
     s = (C.c_float * 3)(*std)
     e0 = _begin()
     check(_lib.load().ca_preprocess_u8(ptr(images_hwc), ptr(patches), B, S, m, s, stream_ptr()), "ca_preprocess_u8")
-    _end(e0, "preprocess_u8", 2, float(images_hwc.numel() + patches.numel() * 2))
+    _end(e0, "preprocess_u8", 1, float(images_hwc.numel() + patches.numel() * 2))
     return patches
 
 
@@ -197,11 +197,14 @@ def rowstats_merge(pm, ps, weight, rmax, rinv, wtab=None):
 
 
 def colsum_e(E, wtab, pc, B, N):
-    """pc[B, N, P] column-sum partials of the (weighted) row softmax from the stored fp16 exponentials E [B, N, lde]."""
+    """pc[B, P, N] (span-major) column-sum partials of the (weighted) row softmax from the stored fp16 exponentials
+    E [B, N, lde]."""
     _req(E, torch.float16, "E")
     _req(wtab, torch.float32, "wtab")
     _req(pc, torch.float32, "pc")
-    P = pc.shape[-1]
+    P = pc.shape[-2]
+    if pc.shape[-1] != N or wtab.shape[-1] != P:
+        raise ValueError("colsum_e: pc must be [B, P, N] with P = wtab.shape[-1]")
     e0 = _begin()
     check(_lib.load().ca_colsum_e(ptr(E), E.stride(-2), E.stride(0), ptr(wtab), ptr(pc), B, N, P, stream_ptr()),
           "ca_colsum_e")
@@ -210,8 +213,9 @@ def colsum_e(E, wtab, pc, B, N):
 
 def focal_finalize(pc, cbias, attn, rs_in, rs_out, B, N, focus_strength=1.5, mode=0, cur_weight=None,
                    adaptive_weight=0.5):
-    """cur_weight [B] (optional) + adaptive_weight: the curiosity modulation of src/model.py:264-276."""
-    P = pc.shape[-1]
+    """pc [B, P, N] span-major partials; cur_weight [B] (optional) + adaptive_weight: the curiosity modulation of
+    src/model.py:264-276."""
+    P = pc.shape[-2]
     _req(cur_weight, torch.float32, "cur_weight")
     e0 = _begin()
     check(_lib.load().ca_focal_finalize(ptr(pc), ptr(cbias), ptr(attn), ptr(rs_in), ptr(rs_out), B, N, P,

@@ -95,11 +95,13 @@ int ca_fetch_pinned_f32(float* dst, const float* h_src_pinned, size_t n, void* s
 int ca_rowstats_merge(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, float* wtab,
                       int rows, int P, void* stream);
 /* Column sums of the (weighted) row softmax from the span-relative exponentials E (fp16 [B, N, lde], written by
- * ca_gemm_bf16 with CA_EPI_ROWSTATS when `out` is given): pc[b, j, p] = sum_{i in row span p} E[b,i,j] * wtab[b,i,j/64].
+ * ca_gemm_bf16 with CA_EPI_ROWSTATS when `out` is given): pc[b, p, j] = sum_{i in row span p} E[b,i,j] * wtab[b,i,j/64]
+ * (span-major [B, P, N]: every CTA writes one contiguous row).
  * Replaces the second Q K^T pass (CA_EPI_COLSUM) by one bandwidth-bound read of E.  src/model.py:234 (col mean), :308. */
 int ca_colsum_e(const uint16_t* E, int lde, long long e_batch_stride, const float* wtab, float* pc, int B, int N, int P,
                 void* stream);
-/* mode 0: FocalStream attention from CA_EPI_COLSUM partials: mean over rows + centre bias, L1 normalise, clamp 1e-8,
+/* pc: the span-major [B, P, N] partials of ca_colsum_e.
+ * mode 0: FocalStream attention: mean over rows + centre bias, L1 normalise, clamp 1e-8,
  *         renormalise; optionally rs_out = rs_in * (1 + focus_strength * attn)   (src/model.py:234-282, :426).
  * mode 1: attn = plain sum of the partials (weighted column sums of the un-guided value path). */
 /*         cur_weight (optional, [B]) with adaptive_weight: the curiosity modulation of src/model.py:264-276,

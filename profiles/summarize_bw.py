@@ -27,7 +27,7 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_{tag}_bw*.nc
            "grid": find("launch__grid_size"), "block": find("launch__block_size"),
            "l2": find("lts__t_sector_hit_rate.pct")}
     for r in rows[2:]:
-        name = re.sub(r"\(.*", "", r[find("Kernel Name")]).replace("ca::<unnamed>::", "").replace("void ", "")
+        name = re.sub(r"\(.*", "", r[find("Kernel Name")]).replace("ca::<unnamed>::", "").replace("unnamed>::", "").replace("void ", "")
 
         def num(k):
             i = idx[k]

@@ -144,9 +144,9 @@ def test_focal_colsum_from_stored_exponentials(cuda_device, N, D):
     ref = torch.softmax(s, dim=-1)
     for weight in (None, torch.rand(B, N, device=cuda_device)):
         wtab = torch.empty((B, N, P), device=cuda_device)
-        pc = torch.zeros((B, N, P), device=cuda_device)
+        pc = torch.zeros((B, P, N), device=cuda_device)   # span-major partials
         ops.rowstats_merge(pm, ps, weight, None, None, wtab)
         ops.colsum_e(E, wtab, pc, B, N)
-        got = pc.sum(-1)
+        got = pc.sum(1)
         want = ref.sum(dim=1) if weight is None else (ref * weight[:, :, None]).sum(dim=1)
         assert torch.allclose(got, want, rtol=3e-3, atol=1e-6), ((got - want).abs() / want).max()

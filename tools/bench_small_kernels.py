@@ -13,7 +13,7 @@ B, S = 32, 518
 g = S // 14
 N, T, D = g * g, g * g + 1, 768
 PEAK = 6539.9
-flush = torch.empty(160 * 1024 * 1024, dtype=torch.int8, device=dev)
+flush = torch.zeros(40 * 1024 * 1024, dtype=torch.int32, device=dev)   # 160 MB > the 126 MB L2
 
 
 def timed(name, fn, bytes_alg, reps=10):
@@ -24,7 +24,8 @@ def timed(name, fn, bytes_alg, reps=10):
         return
     tot = 0.0
     for _ in range(reps):
-        flush.zero_()
+        flush.sum()   # READ 160 MB: evicts the kernel's inputs and leaves clean lines (a write would leave 126 MB of dirty
+                      # lines whose write-back then competes with the timed kernel's reads)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
@@ -60,7 +61,7 @@ timed("focal_input", lambda: ops.focal_input(tokens, pe, rs, xin, B, N, D), B * 
 P = ops.stats_partials(N)
 E = (torch.rand(B, N, 64 * ((N + 63) // 64), device=dev) * 0.9 + 0.05).half()
 wtab = torch.rand(B, N, P, device=dev)
-pc = torch.empty(B, N, P, device=dev)
+pc = torch.empty(B, P, N, device=dev)
 timed("colsum_e", lambda: ops.colsum_e(E, wtab, pc, B, N), B * N * N * 2 + wtab.numel() * 4 + pc.numel() * 4)
 heat = torch.softmax(torch.randn(B, N, device=dev), -1)
 pool = torch.empty(B, 32, D, device=dev)
