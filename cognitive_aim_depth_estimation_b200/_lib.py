@@ -85,6 +85,8 @@ _SIGNATURES = {
     "ca_resize_u8": [c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr],
     "ca_jpeg_info": [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "ca_jpeg_decode": [C.c_char_p, C.c_size_t, c_ptr, C.c_int, C.c_int, c_ptr],
+    "ca_jpeg_decode_batch": [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.POINTER(C.c_void_p),
+                             C.POINTER(C.c_int), C.POINTER(C.c_int), c_ptr],
     "ca_focus_map": [c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr],
     "ca_guided_softmax": [c_ptr, c_ptr, C.c_longlong, c_ptr, c_ptr, C.c_int, C.c_int, C.c_float, C.c_float, c_ptr],
     "ca_weighted_pool": [c_ptr, C.c_longlong, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr],

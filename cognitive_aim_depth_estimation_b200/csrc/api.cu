@@ -180,6 +180,11 @@ int ca_jpeg_decode(const uint8_t* h_data, size_t len, uint8_t* out_rgb, int widt
   return ca::jpeg_decode(h_data, len, out_rgb, width, height, static_cast<cudaStream_t>(stream));
 }
 
+int ca_jpeg_decode_batch(const uint8_t* const* h_data, const size_t* lens, int n, uint8_t* const* outs, const int* widths,
+                         const int* heights, void* stream) {
+  return ca::jpeg_decode_batch(h_data, lens, n, outs, widths, heights, static_cast<cudaStream_t>(stream));
+}
+
 int ca_focus_map(const float* heat, int B, int g, int out_h, int out_w, float* norm, float* out, void* stream) {
   return ca::focus_map_launch(heat, B, g, out_h, out_w, norm, out, static_cast<cudaStream_t>(stream));
 }

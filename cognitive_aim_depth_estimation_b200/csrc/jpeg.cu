@@ -10,6 +10,7 @@
 #include <nvjpeg.h>
 
 #include <mutex>
+#include <vector>
 
 #include "host.h"
 
@@ -22,8 +23,13 @@ struct NvJpeg {
   decltype(&nvjpegJpegStateCreate) state_create = nullptr;
   decltype(&nvjpegGetImageInfo) info = nullptr;
   decltype(&nvjpegDecode) decode = nullptr;
+  decltype(&nvjpegDecodeBatchedInitialize) batched_init = nullptr;
+  decltype(&nvjpegDecodeBatched) batched = nullptr;
   nvjpegHandle_t handle = nullptr;
   nvjpegJpegState_t state[64] = {};  // one decoder state per device (calls on one device are serialised by the caller)
+  nvjpegJpegState_t bstate[64] = {};  // ... and one state for the batched decoder, initialised for bstate_n[dev] images
+  int bstate_n[64] = {};
+  std::mutex mu;
   bool ok = false;
   std::string why;
 };
@@ -44,6 +50,8 @@ NvJpeg& nvjpeg() {
     nj.state_create = reinterpret_cast<decltype(nj.state_create)>(dlsym(nj.lib, "nvjpegJpegStateCreate"));
     nj.info = reinterpret_cast<decltype(nj.info)>(dlsym(nj.lib, "nvjpegGetImageInfo"));
     nj.decode = reinterpret_cast<decltype(nj.decode)>(dlsym(nj.lib, "nvjpegDecode"));
+    nj.batched_init = reinterpret_cast<decltype(nj.batched_init)>(dlsym(nj.lib, "nvjpegDecodeBatchedInitialize"));
+    nj.batched = reinterpret_cast<decltype(nj.batched)>(dlsym(nj.lib, "nvjpegDecodeBatched"));
     if (!nj.create || !nj.state_create || !nj.info || !nj.decode) {
       nj.why = "nvJPEG symbols missing";
       return;
@@ -104,6 +112,50 @@ int jpeg_decode(const uint8_t* h_data, size_t len, uint8_t* out_rgb, int width, 
   const nvjpegStatus_t st = nj.decode(nj.handle, nj.state[dev], h_data, len, NVJPEG_OUTPUT_RGBI, &dst, stream);
   if (st != NVJPEG_STATUS_SUCCESS) {
     set_error("jpeg_decode: nvjpegDecode failed with status " + std::to_string(static_cast<int>(st)));
+    return 2;
+  }
+  return 0;
+}
+
+// demo.py:406-432 (`predict_batch`) opens its files one by one; here n JPEG streams are handed to nvJPEG's batched
+// decoder in ONE call (host-side Huffman decoding of the whole batch on a thread pool, one set of GPU kernels for all
+// images) instead of n nvjpegDecode calls from a Python loop.
+int jpeg_decode_batch(const uint8_t* const* h_data, const size_t* lens, int n, uint8_t* const* outs, const int* widths,
+                      const int* heights, cudaStream_t stream) {
+  CA_REQUIRE(h_data && lens && outs && widths && heights && n > 0, "jpeg_decode_batch: null argument");
+  NvJpeg& nj = nvjpeg();
+  if (!nj.ok) return unsupported(nj.why);
+  if (!nj.batched_init || !nj.batched) return unsupported("nvJPEG batched decode entry points missing");
+  for (int i = 0; i < n; ++i) {
+    int w = 0, h = 0;
+    CA_REQUIRE(h_data[i] && lens[i] > 0 && outs[i], "jpeg_decode_batch: null image");
+    CA_TRY(jpeg_info(h_data[i], lens[i], &w, &h, nullptr));
+    CA_REQUIRE(w == widths[i] && h == heights[i], "jpeg_decode_batch: output size does not match the stream");
+  }
+  int dev = 0;
+  CA_CUDA(cudaGetDevice(&dev));
+  CA_REQUIRE(dev >= 0 && dev < 64, "jpeg_decode_batch: device index out of range");
+  std::lock_guard<std::mutex> lock(nj.mu);
+  if (!nj.bstate[dev]) {
+    if (nj.state_create(nj.handle, &nj.bstate[dev]) != NVJPEG_STATUS_SUCCESS) return unsupported("nvjpegJpegStateCreate failed");
+  }
+  if (nj.bstate_n[dev] != n) {
+    const nvjpegStatus_t st = nj.batched_init(nj.handle, nj.bstate[dev], n, 8, NVJPEG_OUTPUT_RGBI);
+    if (st != NVJPEG_STATUS_SUCCESS) {
+      set_error("jpeg_decode_batch: nvjpegDecodeBatchedInitialize failed with status " + std::to_string(static_cast<int>(st)));
+      return 2;
+    }
+    nj.bstate_n[dev] = n;
+  }
+  std::vector<nvjpegImage_t> dst(n);
+  for (int i = 0; i < n; ++i) {
+    dst[i] = nvjpegImage_t{};
+    dst[i].channel[0] = outs[i];
+    dst[i].pitch[0] = static_cast<size_t>(widths[i]) * 3;
+  }
+  const nvjpegStatus_t st = nj.batched(nj.handle, nj.bstate[dev], h_data, lens, dst.data(), stream);
+  if (st != NVJPEG_STATUS_SUCCESS) {
+    set_error("jpeg_decode_batch: nvjpegDecodeBatched failed with status " + std::to_string(static_cast<int>(st)));
     return 2;
   }
   return 0;

@@ -26,12 +26,22 @@ template <bool kU8>
 __global__ void __launch_bounds__(320) patch_rows_kernel(const void* __restrict__ img_v,
                                                           __nv_bfloat16* __restrict__ patches, int S, int g, float3 mean,
                                                           float3 inv_std) {
-  extern __shared__ __align__(16) uint8_t sm[];
+  extern __shared__ __align__(16) uint8_t sm_all[];
+  // uint8 path: the first 3 KB hold lut[c][v] = (v / 255 - mean_c) / std_c, the value ToTensor + Normalize give byte v of
+  // channel c — one shared-memory read instead of an int->float conversion, an IEEE division and an FMA per element
+  float* lut = reinterpret_cast<float*>(sm_all);
+  uint8_t* sm = sm_all + (kU8 ? 3 * 256 * sizeof(float) : 0);
   const int py = blockIdx.x;
   const int b = blockIdx.y;
   const int w = g * kPatch;
   int head = 0;
   if constexpr (kU8) {
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+      const int c = i >> 8;
+      const float m = c == 0 ? mean.x : (c == 1 ? mean.y : mean.z);
+      const float sd = c == 0 ? inv_std.x : (c == 1 ? inv_std.y : inv_std.z);
+      lut[i] = (static_cast<float>(i & 255) / 255.0f - m) * sd;
+    }
     const uint8_t* src = static_cast<const uint8_t*>(img_v) + (static_cast<size_t>(b) * S + py * kPatch) * S * 3;
     const int len = kPatch * S * 3;
     head = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
@@ -73,16 +83,12 @@ __global__ void __launch_bounds__(320) patch_rows_kernel(const void* __restrict_
   uint32_t* out = reinterpret_cast<uint32_t*>(patches + (static_cast<size_t>(b) * g * g + static_cast<size_t>(py) * g) * kPatchKPad) + kp;
   const int step = kU8 ? kPatch * 3 : kPatch;
   if constexpr (kU8) {
-    // (v / 255 - mean) / std as one table look-up per channel and byte value would need 1.5 KB of smem; the arithmetic is
-    // 3 instructions per element, cheaper than the second shared-memory access
-    const float m0 = ch[0] == 0 ? mean.x : (ch[0] == 1 ? mean.y : mean.z);
-    const float m1 = ch[1] == 0 ? mean.x : (ch[1] == 1 ? mean.y : mean.z);
-    const float s0 = ch[0] == 0 ? inv_std.x : (ch[0] == 1 ? inv_std.y : inv_std.z);
-    const float s1 = ch[1] == 0 ? inv_std.x : (ch[1] == 1 ? inv_std.y : inv_std.z);
+    const float* l0 = lut + ch[0] * 256;
+    const float* l1 = lut + ch[1] * 256;
 #pragma unroll 4
     for (int px = 0; px < g; ++px) {
-      const float a = ok[0] ? (static_cast<float>(sm[off[0] + px * step]) / 255.0f - m0) * s0 : 0.f;
-      const float c = ok[1] ? (static_cast<float>(sm[off[1] + px * step]) / 255.0f - m1) * s1 : 0.f;
+      const float a = ok[0] ? l0[sm[off[0] + px * step]] : 0.f;
+      const float c = ok[1] ? l1[sm[off[1] + px * step]] : 0.f;
       out[static_cast<size_t>(px) * kPairs] = pack_bf16x2(a, c);
     }
   } else {
@@ -188,7 +194,7 @@ template <bool kU8>
 static int patch_rows_launch(const void* images, __nv_bfloat16* patches, int B, int S, float3 mean, float3 inv_std,
                              cudaStream_t stream) {
   const int g = S / kPatch;
-  const size_t smem = kU8 ? static_cast<size_t>(kPatch) * S * 3 + 32 : static_cast<size_t>(3) * kPatch * g * kPatch * 2;
+  const size_t smem = kU8 ? static_cast<size_t>(kPatch) * S * 3 + 32 + 3 * 256 * sizeof(float) : static_cast<size_t>(3) * kPatch * g * kPatch * 2;
   CA_REQUIRE(smem <= 200 * 1024, "patchify: image side too large for the shared-memory staging (max ~2400)");
   static PerDeviceOnce configured;  // per instantiation and per device
   CA_TRY(configured.run([&]() -> int {

@@ -931,8 +931,13 @@ class CognitiveAimModel(nn.Module):
             raise RuntimeError("preprocess_jpeg runs only on a CUDA sm_100 device; there is no CPU fallback")
         if len(jpeg_files) == 0:
             raise ValueError("empty list of JPEG files")
-        out = [self.preprocess(ops.jpeg_decode(f, dev).unsqueeze(0), size, mean, std) for f in jpeg_files]
-        return torch.cat(out, dim=0)
+        # one batched nvJPEG decode for all files; images of equal size come back as slices of one [n, H, W, 3] block and
+        # are resized + normalised as one tensor (one launch sequence per distinct source size, not per file)
+        imgs, groups = ops.jpeg_decode_batch(list(jpeg_files), dev, return_groups=True)
+        out = torch.empty(len(imgs), 3, size, size, device=dev, dtype=torch.float32)
+        for block, idx in groups:
+            out[idx] = self.preprocess(block, size, mean, std)
+        return out
 
     @torch.no_grad()
     @_on_own_device

@@ -277,6 +277,48 @@ def jpeg_decode(data: bytes, device=None):
     return out
 
 
+def jpeg_decode_batch(files, device=None, return_groups=False):
+    """List of JPEG files (bytes) -> list of uint8 [H_i, W_i, 3] RGB CUDA tensors, decoded in ONE nvjpegDecodeBatched call
+    (reference demo.py:406-432 `predict_batch` opens and decodes its files one at a time).  Images of equal size share
+    one contiguous [k, H, W, 3] allocation (the returned tensors are its slices); `return_groups=True` also returns
+    [(block [k, H, W, 3], indices into the list)] so that same-sized photographs go to the resize / normalise kernels as
+    one tensor."""
+    import ctypes as C
+    if len(files) == 0:
+        raise ValueError("empty list of JPEG files")
+    datas = []
+    for f in files:
+        if not isinstance(f, (bytes, bytearray, memoryview)):
+            raise ValueError("jpeg_decode_batch expects each file's bytes")
+        datas.append(bytes(f))
+    lib = _lib.load()
+    n = len(datas)
+    ws, hs = (C.c_int * n)(), (C.c_int * n)()
+    for i, d in enumerate(datas):
+        w, h = C.c_int(0), C.c_int(0)
+        check(lib.ca_jpeg_info(d, len(d), C.byref(w), C.byref(h)), "ca_jpeg_info")
+        ws[i], hs[i] = w.value, h.value
+    dev = torch.device(device or "cuda")
+    groups = {}
+    for i in range(n):
+        groups.setdefault((hs[i], ws[i]), []).append(i)
+    outs = [None] * n
+    blocks = []
+    for (h, w), idx in groups.items():
+        block = torch.empty(len(idx), h, w, 3, device=dev, dtype=torch.uint8)
+        blocks.append((block, idx))
+        for j, i in enumerate(idx):
+            outs[i] = block[j]
+    data_arr = (C.c_char_p * n)(*datas)
+    len_arr = (C.c_size_t * n)(*[len(d) for d in datas])
+    out_arr = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    e0 = _begin()
+    with torch.cuda.device(dev):
+        check(lib.ca_jpeg_decode_batch(data_arr, len_arr, n, out_arr, ws, hs, stream_ptr()), "ca_jpeg_decode_batch")
+    _end(e0, "jpeg", 1, float(sum(o.numel() for o in outs)))
+    return (outs, blocks) if return_groups else outs
+
+
 def focus_map(heat, g, out_h, out_w, norm, out):
     """norm [B, g*g], out [B, out_h, out_w] (or None): heat-map post-processing of demo.py:530-563 (csrc/visual.cu)."""
     _req(heat, torch.float32, "heat")

@@ -222,6 +222,11 @@ int ca_resize_u8(const uint8_t* src, int B, int H0, int W0, int out_h, int out_w
  * here the results agree to <= 5 LSB (mean ~0.6), not bit for bit (tests/test_jpeg_gpu.py states the tolerance). */
 int ca_jpeg_info(const uint8_t* h_data, size_t len, int* width, int* height);
 int ca_jpeg_decode(const uint8_t* h_data, size_t len, uint8_t* out_rgb, int width, int height, void* stream);
+/* n JPEG files in ONE call (nvjpegDecodeBatched: the Huffman stage of the whole batch on a host thread pool, one set of
+ * GPU kernels): h_data[i] / lens[i] host bytes, outs[i] device RGB HWC buffers of widths[i] x heights[i] (from
+ * ca_jpeg_info).  Replaces the per-file loop of reference demo.py:406-432 (`predict_batch`). */
+int ca_jpeg_decode_batch(const uint8_t* const* h_data, const size_t* lens, int n, uint8_t* const* outs, const int* widths,
+                         const int* heights, void* stream);
 
 /* ---- visualisation post-processing (the consumer right after the hot path; replaces demo.py:530-563) ------------
  * norm[b, :]  = min-max( where(a > percentile70(a), a, 0.3 a) ),  a = heat[b, :]^3            (numpy float32 semantics)
