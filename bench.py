@@ -240,6 +240,68 @@ def other_configs(model, dev, local_rank: int, ex_fn, img_fn):
     ms, k, ck = _timed_region(guided, local_rank)
     entry("configs[3] per-GPU shape", "full cognitive model + EXIF, guided forward, 64 images per call", B, S_, ms, k, ck,
           ALGO_GFLOP_BY_SIZE[518])
+    # the same shape through the handle-level C-ABI (one native call per forward: csrc/launcher.cu), and the single-image
+    # latency of configs[0]'s shape through both front ends
+    from cognitive_aim_depth_estimation_b200.native import NativeModel
+    nat = NativeModel({k: v.detach() for k, v in model.state_dict().items()}, device=dev)
+    side = torch.cuda.Stream(device=dev)
+
+    def native_guided(i):
+        with torch.cuda.stream(side):
+            torch.manual_seed(11)
+            return nat.forward_with_guidance(imgs[i % 3], ex, INSTRUCTIONS[i % 9])
+
+    def on_side(fn):
+        def run(i):
+            with torch.cuda.stream(side):
+                return fn(i)
+        return run
+
+    def timed_on_side(fn):
+        side.wait_stream(torch.cuda.current_stream())
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k = 20
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        with torch.cuda.stream(side):
+            e0.record()
+        for i in range(k):
+            fn(i)
+        with torch.cuda.stream(side):
+            e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k, k, sampler.stop()
+
+    ms, k, ck = timed_on_side(native_guided)
+    entry("handle-level C-ABI, 64 images", "ca_forward_guided (one native call per forward), same inputs", B, S_, ms, k, ck,
+          ALGO_GFLOP_BY_SIZE[518], gpu_launches_per_call=nat.launch_count())
+    one = imgs[0][:1].contiguous()
+    ex1 = {kk: v[:1].contiguous() for kk, v in ex.items()}
+
+    def py_one(i):
+        torch.manual_seed(11)
+        return model.forward_with_guidance(one, ex1, INSTRUCTIONS[i % 9], return_attention=True)
+
+    def nat_one(i):
+        with torch.cuda.stream(side):
+            torch.manual_seed(11)
+            return nat.forward_with_guidance(one, ex1, INSTRUCTIONS[i % 9])
+
+    for name, fn in (("single image, Python front end", py_one), ("single image, handle-level C-ABI", nat_one)):
+        side.wait_stream(torch.cuda.current_stream())
+        for i in range(5):
+            fn(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(200):
+            fn(i)
+        torch.cuda.synchronize()
+        entry(name, "configs[0] shape: one 518 x 518 image per call, wall clock per call (device-bound: ~110 dependent "
+              "launches of 5-20 us each in one CUDA graph)", 1, S_, (time.perf_counter() - t0) / 200 * 1e3, 200, None)
+    nat.close()
     del imgs
     # configs[4]: 1036 x 1036 (4x tokens), 8 images per call
     B, S_ = 8, 1036

@@ -60,6 +60,38 @@ class CuriosityModWeights(C.Structure):
                 ("mod_b1", C.c_void_p * 8)]
 
 
+class LayerWeights(C.Structure):
+    """ca_layer_weights (include/cogaim_b200.h)."""
+    _names = ["n1w", "n1b", "wqkv", "bqkv", "wo", "bo", "ls1", "n2w", "n2b", "w1", "b1", "w2", "b2", "ls2"]
+    _fields_ = [(n, C.c_void_p) for n in _names]
+
+
+class FocalWeights(C.Structure):
+    """ca_focal_weights (include/cogaim_b200.h)."""
+    _names = ["wqk", "bqk", "wv", "bv", "pw0", "pb0", "pw1", "pb1"]
+    _fields_ = [(n, C.c_void_p) for n in _names]
+
+
+class ModelWeights(C.Structure):
+    """ca_model_weights (include/cogaim_b200.h)."""
+    _fields_ = [("patch_w", C.c_void_p), ("patch_b", C.c_void_p), ("cls_token", C.c_void_p), ("pos_embed", C.c_void_p),
+                ("layer", LayerWeights * 12), ("lnw", C.c_void_p), ("lnb", C.c_void_p), ("n_focal", C.c_int),
+                ("focus_strength", C.c_float), ("focal", FocalWeights * 4), ("ffw0", C.c_void_p), ("ffb0", C.c_void_p),
+                ("ffw1", C.c_void_p), ("ffb1", C.c_void_p), ("heads", HeadsWeights), ("curiosity", CuriosityWeights),
+                ("exploration_history", C.c_void_p), ("history_len", C.c_int), ("history_pointer", C.c_void_p),
+                ("num_cameras", C.c_int)]
+
+
+class ForwardCall(C.Structure):
+    """ca_forward_call (include/cogaim_b200.h)."""
+    _fields_ = [("images", C.c_void_p), ("images_u8", C.c_int), ("B", C.c_int), ("S", C.c_int), ("exif", C.c_void_p),
+                ("camera_idx", C.c_void_p), ("instruction", C.c_char_p), ("mask", C.c_void_p),
+                ("mask_batch_stride", C.c_longlong), ("tmp_w", C.c_void_p), ("tmp_b", C.c_void_p), ("eps", C.c_void_p),
+                ("noise", C.c_void_p), ("curiosity_runs", C.c_int), ("depth", C.c_void_p), ("conf", C.c_void_p),
+                ("attention", C.c_void_p), ("argmax", C.c_void_p), ("fused", C.c_void_p), ("fault", C.c_void_p),
+                ("use_graph", C.c_int)]
+
+
 # name -> (argtypes); every function returns int status except where noted
 _SIGNATURES = {
     "ca_version": [],
@@ -93,6 +125,12 @@ _SIGNATURES = {
     "ca_heads": [C.POINTER(HeadsWeights), C.POINTER(HeadsInputs), c_ptr, c_ptr, c_ptr, C.c_int, c_ptr],
     "ca_focal_value": [C.POINTER(FocalValueArgs), C.c_int, c_ptr],
     "ca_focal_fusion": [c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr],
+    "ca_create": [C.POINTER(C.c_void_p), C.POINTER(ModelWeights), C.c_int],
+    "ca_destroy": [c_ptr],
+    "ca_forward_guided": [c_ptr, C.POINTER(ForwardCall), c_ptr],
+    "ca_forward": [c_ptr, C.POINTER(ForwardCall), c_ptr],
+    "ca_backbone": [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr],
+    "ca_last_launch_count": [c_ptr],
 }
 
 

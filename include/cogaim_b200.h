@@ -234,6 +234,99 @@ int ca_jpeg_decode_batch(const uint8_t* const* h_data, const size_t* lens, int n
  * heat, norm: [B, g*g] fp32; out: [B, out_h, out_w] fp32.  g*g <= 16384. */
 int ca_focus_map(const float* heat, int B, int g, int out_h, int out_w, float* norm, float* out, void* stream);
 
+/* ================================================================================================
+ * Handle-level entry points: the whole forward behind ONE call.
+ *
+ * The per-kernel entry points above are what the tests drive; a host that is not Python (or that wants no per-kernel
+ * orchestration) creates a handle from a table of packed device weights and calls ca_forward_guided / ca_forward.  The
+ * handle owns what the reference keeps in Python objects between calls: the per-resolution tables (position-embedding
+ * interpolation, focal position encoding, centre bias, instruction masks — reference src/model.py:140-231, 1270-1376,
+ * HF modeling_dinov2.py:57-95), the activation workspace per (batch, resolution), a ring of pinned staging buffers for the
+ * per-call host inputs, a side stream for the CuriosityModule branch and one CUDA graph per (path, batch, resolution).
+ * One handle per device; calls on one handle must be serialised by the caller (the reference is single-threaded too,
+ * demo.py:79,338).  Replaces the flow of reference demo.py:298-405 (`predict`) / src/model.py:1157-1240, 1064-1155.
+ * ================================================================================================ */
+typedef struct ca_handle ca_handle;
+
+/* DEVICE pointers to one encoder layer's operands: bf16 GEMM weights [out, in] (torch Linear layout), fp32 the rest. */
+typedef struct ca_layer_weights {
+  const float *n1w, *n1b;       /* norm1                                                    HF modeling_dinov2.py:354 */
+  const uint16_t* wqkv;         /* [2304, 768] = query | key | value weights stacked         HF:203-214 */
+  const float* bqkv;            /* [2304] */
+  const uint16_t* wo;           /* attention.output.dense [768, 768]                         HF:246 */
+  const float *bo, *ls1;        /* bias, layer_scale1.lambda1                                HF:278 */
+  const float *n2w, *n2b;       /* norm2 */
+  const uint16_t* w1;           /* mlp.fc1 [3072, 768] */
+  const float* b1;
+  const uint16_t* w2;           /* mlp.fc2 [768, 3072] */
+  const float *b2, *ls2;
+} ca_layer_weights;
+
+typedef struct ca_focal_weights {
+  const uint16_t* wqk;          /* [1536, 768] = query_proj | key_proj of one FocalStream      src/model.py:192-193 */
+  const float* bqk;             /* [1536] */
+  const float *wv, *bv;         /* value_proj [768,768], [768] fp32 (un-guided features only)  :194 */
+  const float *pw0, *pb0, *pw1, *pb1; /* projection.{0,3} [256,768] [64,256]                   :311 */
+} ca_focal_weights;
+
+typedef struct ca_model_weights {
+  const uint16_t* patch_w;      /* [768, 592] bf16: conv weight flattened (c, ky, kx), columns 588..591 zero */
+  const float* patch_b;         /* [768] */
+  const float* cls_token;       /* [768] */
+  const float* pos_embed;       /* HOST pointer, fp32 [1 + 37*37, 768]: the native-grid position embedding (row 0 = CLS);
+                                   interpolated per resolution by the handle */
+  ca_layer_weights layer[12];
+  const float *lnw, *lnb;       /* backbone.layernorm */
+  int n_focal;                  /* focal iterations (1..4) */
+  float focus_strength;         /* src/model.py:426 re-focus strength (1.5 under every shipped YAML) */
+  ca_focal_weights focal[4];
+  const float *ffw0, *ffb0, *ffw1, *ffb1;   /* focal_stream.fusion.{0,2}  [128,192] [64,128]   :430 */
+  ca_heads_weights heads;
+  ca_curiosity_weights curiosity;
+  float* exploration_history;   /* curiosity_module.exploration_history (device, mutated)      :760-773 */
+  int history_len;
+  long long* history_pointer;   /* device int64 */
+  int num_cameras;              /* rows of heads.cam_emb; 0 = the model has no EXIF prior */
+} ca_model_weights;
+
+/* Per-call inputs.  Device pointers unless marked HOST.  The two Gaussian draws of the CuriosityModule and the per-call
+ * random projection come from the caller because the reference takes them from ITS global generator (src/model.py:609,
+ * 744, 1421): parity under a shared seed is the caller's RNG, not this library's. */
+typedef struct ca_forward_call {
+  const void* images;           /* fp32 [B,3,S,S] normalised, or (images_u8) uint8 [B,S,S,3] at model resolution */
+  int images_u8;
+  int B, S;
+  const float* exif;            /* [B,3] raw focal_length, aperture, iso; NULL = no EXIF (zero slot; un-guided only) */
+  const long long* camera_idx;  /* [B] */
+  const char* instruction;      /* guided: one of the 9 instructions / aliases (HOST string); NULL when `mask` is given */
+  const float* mask;            /* guided: explicit guidance [N] (mask_batch_stride 0) or per image [B,N] (stride N) */
+  long long mask_batch_stride;
+  const float* tmp_w;           /* HOST [64,768]: per-call projection weight (guided only)       src/model.py:1421 */
+  const float* tmp_b;           /* HOST [64] */
+  const float* eps;             /* HOST [runs,B,192]: CuriosityModule draw of :609, one per run (guided: 1 run) */
+  const float* noise;           /* HOST [runs,B,768]: draw of :744 */
+  int curiosity_runs;           /* un-guided: 1..3 runs as the reference makes them (:992, :1104, :1138); guided: 1 */
+  float* depth;                 /* out [B] */
+  float* conf;                  /* out [B] */
+  float* attention;             /* out [B,N]: guided heat map / last-iteration focal attention */
+  int* argmax;                  /* out [B] (guided) or NULL */
+  float* fused;                 /* out [B,192] fusion features (un-guided) or NULL */
+  int* fault;                   /* optional device-visible word: bit 0 = camera_idx out of range */
+  int use_graph;                /* 1: capture the launch sequence once per (path, B, S) and replay it */
+} ca_forward_call;
+
+/* `w` (HOST struct of device pointers) is copied; the weights themselves must outlive the handle. */
+int ca_create(ca_handle** out, const ca_model_weights* w, int device);
+int ca_destroy(ca_handle* h);
+/* forward_with_guidance(images, exif, instruction | guidance tensor) -> depth, confidence, heat map, arg-max cell. */
+int ca_forward_guided(ca_handle* h, const ca_forward_call* call, void* stream);
+/* forward(images, exif or none) -> depth, confidence, last-iteration focal attention, fusion features. */
+int ca_forward(ca_handle* h, const ca_forward_call* call, void* stream);
+/* DINOv2 tokens only: tokens_out fp32 [B, 1+N, 768] (BASELINE.json configs[2]). */
+int ca_backbone(ca_handle* h, const void* images, int images_u8, int B, int S, float* tokens_out, void* stream);
+/* kernels launched by the last ca_forward* / ca_backbone call of this handle (the launch-count claim of bench.py). */
+int ca_last_launch_count(const ca_handle* h);
+
 #ifdef __cplusplus
 }
 #endif
