@@ -100,10 +100,12 @@ _SIGNATURES = {
                      C.c_longlong, C.c_int, c_ptr, C.c_int, C.c_longlong, c_ptr, c_ptr, c_ptr, C.c_int, C.c_float,
                      c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "ca_attention_bf16": [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr],
+    "ca_attention_bf16_ld": [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr],
     "ca_patchify_f32": [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr],
     "ca_preprocess_u8": [c_ptr, c_ptr, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), c_ptr],
     "ca_cls_rows": [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr],
     "ca_layernorm": [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr],
+    "ca_layernorm_ld": [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr],
     "ca_focal_input": [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr],
     "ca_fetch_pinned_f32": [c_ptr, c_ptr, C.c_size_t, c_ptr],
     "ca_rowstats_merge": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr],

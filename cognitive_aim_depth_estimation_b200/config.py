@@ -31,6 +31,7 @@ class EffectiveConfig:
     focal_hidden_dim: int
     enable_hierarchical_curiosity: bool
     lora_merge_target: Optional[str] = None  # NOT a reference key: see model.CognitiveAimModel._lora_delta
+    lora_mode: str = "merge"  # NOT a reference key: "merge" (into the packed weight) or "fused" (extra K columns of the GEMM)
     fusion_dim: int = 192  # src/model.py:904-905
 
 
@@ -60,4 +61,5 @@ def effective_config(config: dict, camera_info: Optional[dict] = None) -> Effect
         focal_hidden_dim=int(config.get("focal_hidden_dim", 256)),  # :859
         enable_hierarchical_curiosity=bool(config.get("enable_hierarchical_curiosity", True)),  # :951
         lora_merge_target=config.get("lora_merge_target"),
+        lora_mode=str(config.get("lora_mode", "merge")),
     )

@@ -77,6 +77,11 @@ int ca_attention_bf16(const uint16_t* qkv, uint16_t* out, int B, int T, int H, v
                               H, static_cast<cudaStream_t>(stream));
 }
 
+int ca_attention_bf16_ld(const uint16_t* qkv, uint16_t* out, int ldo, int B, int T, int H, void* stream) {
+  return ca::attention_launch(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), B, T,
+                              H, static_cast<cudaStream_t>(stream), ldo);
+}
+
 int ca_patchify_f32(const float* images, uint16_t* patches, int B, int S, void* stream) {
   return ca::patchify_f32_launch(images, reinterpret_cast<__nv_bfloat16*>(patches), B, S,
                                  static_cast<cudaStream_t>(stream));
@@ -95,6 +100,11 @@ int ca_cls_rows(float* x, const float* cls, const float* pos, int B, int T, int 
 int ca_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_is_bf16, int rows, int D,
                  float eps, void* stream) {
   return ca::layernorm_launch(x, gamma, beta, out, out_is_bf16, rows, D, eps, static_cast<cudaStream_t>(stream));
+}
+
+int ca_layernorm_ld(const float* x, const float* gamma, const float* beta, void* out, int out_is_bf16, int ld_out,
+                    int rows, int D, float eps, void* stream) {
+  return ca::layernorm_launch(x, gamma, beta, out, out_is_bf16, rows, D, eps, static_cast<cudaStream_t>(stream), ld_out);
 }
 
 int ca_focal_input(const float* tokens, const float* pe, const float* rowscale, uint16_t* xin, int B, int N, int D,

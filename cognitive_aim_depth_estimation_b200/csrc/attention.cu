@@ -568,7 +568,7 @@ std::mutex g_mu;
 
 }  // namespace
 
-int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, cudaStream_t stream) {
+int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, cudaStream_t stream, int ldo) {
   CA_REQUIRE(qkv && out, "attention: null pointer");
   CA_REQUIRE(B > 0 && T > 0 && H > 0, "attention: non-positive dimension");
   const int ld = 3 * H * kHeadDim;
@@ -597,7 +597,8 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
   a.qkv = qkv;
   a.ld = ld;
   a.out = out;
-  a.ldo = H * kHeadDim;
+  a.ldo = ldo > 0 ? ldo : H * kHeadDim;
+  CA_REQUIRE(a.ldo >= H * kHeadDim && a.ldo % 8 == 0, "attention: output leading dimension must be >= H*64 and a multiple of 8");
   const int grid = a.n_items < 2 * st.sms ? a.n_items : 2 * st.sms;  // persistent: two CTAs per SM
   // Every launch owns one slot of a per-device ring of work counters, zeroed on ITS stream right before the kernel (a
   // memset node when the launch is captured into a graph): launches that overlap on different streams never share a

@@ -119,7 +119,7 @@ __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__
 template <int D, typename OutT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, OutT* __restrict__ out, int rows,
-                                                         float eps) {
+                                                         float eps, int ld_out) {
   constexpr int kVec = D / 128;  // float4 per lane
   const int row = blockIdx.x * (blockDim.x >> 5) + warp_id();
   if (row >= rows) return;
@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     y.w = (v[i].w - mean) * rstd * g.w + be.w;
     if constexpr (sizeof(OutT) == 2) {
       uint2 w = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
-      reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * D)[lane + 32 * i] = w;
+      reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * ld_out)[lane + 32 * i] = w;
     } else {
-      reinterpret_cast<float4*>(out + static_cast<size_t>(row) * D)[lane + 32 * i] = y;
+      reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ld_out)[lane + 32 * i] = y;
     }
   }
 }
@@ -249,16 +249,18 @@ int cls_rows_launch(float* x, const float* cls, const float* pos, int B, int T, 
 }
 
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, int out_is_bf16, int rows, int D,
-                     float eps, cudaStream_t stream) {
+                     float eps, cudaStream_t stream, int ld_out) {
   CA_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
+  if (ld_out <= 0) ld_out = D;
+  CA_REQUIRE(ld_out >= D && ld_out % (out_is_bf16 ? 4 : 4) == 0, "layernorm: output leading dimension must be >= D and keep rows 8/16-byte aligned");
   CA_REQUIRE(D == 768, "layernorm: only D = 768 (ViT-B) is instantiated");
   CA_REQUIRE(rows > 0, "layernorm: no rows");
   const int grid = (rows + 7) / 8;
   if (out_is_bf16)
     layernorm_kernel<768, __nv_bfloat16><<<grid, 256, 0, stream>>>(x, gamma, beta, static_cast<__nv_bfloat16*>(out),
-                                                                   rows, eps);
+                                                                   rows, eps, ld_out);
   else
-    layernorm_kernel<768, float><<<grid, 256, 0, stream>>>(x, gamma, beta, static_cast<float*>(out), rows, eps);
+    layernorm_kernel<768, float><<<grid, 256, 0, stream>>>(x, gamma, beta, static_cast<float*>(out), rows, eps, ld_out);
   CA_CUDA(cudaGetLastError());
   return 0;
 }

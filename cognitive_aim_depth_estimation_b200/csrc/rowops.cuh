@@ -15,7 +15,7 @@ int preprocess_u8_launch(const uint8_t* images, __nv_bfloat16* patches, int B, i
 int fetch_pinned_launch(float* dst, const float* src_pinned_host, size_t n, cudaStream_t stream);
 int cls_rows_launch(float* x, const float* cls, const float* pos, int B, int T, int D, cudaStream_t stream);
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, int out_is_bf16, int rows, int D,
-                     float eps, cudaStream_t stream);
+                     float eps, cudaStream_t stream, int ld_out = 0);  // ld_out: output row pitch in elements (0 = D)
 int focal_input_launch(const float* tokens, const float* pe, const float* rowscale, __nv_bfloat16* xin, int B, int N,
                        int D, cudaStream_t stream);
 

@@ -38,6 +38,7 @@ _LAYERS = 12
 _MLP = 3072
 _POOL_SPLITS = 32  # 1024 CTAs at B = 32: the 8-way split (256 CTAs) reached 39 % of the HBM rate (profiles/r01e_bw_kernels.md)
 _MAX_CURIOSITY_RUNS = 3
+_LORA_PAD = 64  # fused LoRA: the rank is padded to one 64-wide K block of the tcgen05 GEMM (K = 768 + 64 = 13 blocks)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -164,6 +165,12 @@ class CognitiveAimModel(nn.Module):
             raise ValueError("lora_merge_target must be one of query / key / value / attention_output")
         if cfg.lora_merge_target and not cfg.use_lora:
             raise ValueError("lora_merge_target needs use_lora: true")
+        if cfg.lora_mode not in ("merge", "fused"):
+            raise ValueError("lora_mode must be 'merge' or 'fused'")
+        if cfg.lora_mode == "fused" and not cfg.lora_merge_target:
+            raise ValueError("lora_mode: fused needs lora_merge_target (which projection the adapters apply to)")
+        if cfg.lora_mode == "fused" and cfg.lora_rank > _LORA_PAD:
+            raise ValueError(f"lora_mode: fused supports ranks up to {_LORA_PAD}")
         self.use_ambient, self.use_focal = cfg.use_ambient, cfg.use_focal
         self.use_iterative, self.use_exif = cfg.use_iterative, cfg.use_exif
         self.target_fusion_dim = 768
@@ -221,11 +228,37 @@ class CognitiveAimModel(nn.Module):
         projection's weight when the bf16 operands are packed: on an inference path with one adapter set this is
         exactly the LoRA output at zero extra HBM traffic, FLOPs or launches, which no epilogue-fused rank-16 MMA step
         can beat (that form only pays when adapters change per request, which the reference cannot express)."""
-        if not self.cfg.use_lora or self.cfg.lora_merge_target != target:
+        if not self.cfg.use_lora or self.cfg.lora_merge_target != target or self.cfg.lora_mode != "merge":
             return None
         A = sd[f"lora_layers.{layer}.lora_A"].float()
         Bm = sd[f"lora_layers.{layer}.lora_B"].float()
         return (16.0 / self.cfg.lora_rank) * (Bm @ A)  # alpha defaults to 16 (:15), scaling = alpha / rank (:19)
+
+    def _lora_fused(self) -> bool:
+        return self.cfg.use_lora and self.cfg.lora_mode == "fused"
+
+    def _write_lora(self, L, A, Bm):
+        """Adapter (A [r, 768], B [768, r]) -> the packed operands of one layer: rows of `lora_a`, and the extra K columns
+        of the target projection's weight, (alpha / r) * B in the rows of the adapted projection (zero elsewhere)."""
+        r = self.cfg.lora_rank
+        tgt = self.cfg.lora_merge_target
+        dev = L["lora_a"].device
+        L["lora_a"].zero_()
+        L["lora_a"][:r] = A.detach().to(dev, torch.bfloat16)
+        key = "wo_ext" if tgt == "attention_output" else "wqkv_ext"
+        row0 = {"query": 0, "key": _D, "value": 2 * _D, "attention_output": 0}[tgt]
+        L[key][:, _D:] = 0
+        L[key][row0:row0 + _D, _D:_D + r] = ((16.0 / r) * Bm.detach().float()).to(dev, torch.bfloat16)
+
+    def set_lora_adapters(self, adapters):
+        """lora_mode: fused only — swap the adapters of some or all encoder layers WITHOUT re-packing the base weights:
+        `adapters` maps layer index -> (lora_A [r, 768], lora_B [768, r]).  Takes effect at the next forward (the CUDA
+        graphs read the operands through fixed addresses)."""
+        if not self._lora_fused():
+            raise ValueError("set_lora_adapters needs use_lora: true and lora_mode: fused")
+        pk = self._pack()
+        for i, (A, Bm) in adapters.items():
+            self._write_lora(pk["layers"][i], A, Bm)
 
     def _device(self) -> torch.device:
         return self.backbone.layernorm.weight.device
@@ -268,8 +301,23 @@ class CognitiveAimModel(nn.Module):
                 "w2": b16(sd[p + "mlp.fc2.weight"]), "b2": f32(sd[p + "mlp.fc2.bias"]),
                 "ls2": f32(sd[p + "layer_scale2.lambda1"]),
             }
+            if self._lora_fused():
+                # lora_mode: fused — y = [h | t] [W | s B]^T with t = h A^T: the adapter is ONE extra 64-wide K block of the
+                # projection's tcgen05 GEMM (rank padded with zeros), t written behind each row of the activation by a
+                # small GEMM.  W itself is never touched: `set_lora_adapters` swaps adapters between calls by rewriting
+                # A and the 64 extra columns only.
+                tgt = self.cfg.lora_merge_target
+                key = "wo" if tgt == "attention_output" else "wqkv"
+                base = L[key]
+                ext = torch.zeros(base.shape[0], _D + _LORA_PAD, device=dev, dtype=torch.bfloat16)
+                ext[:, :_D] = base
+                L[key + "_ext"] = ext
+                L["lora_a"] = torch.zeros(_LORA_PAD, _D, device=dev, dtype=torch.bfloat16)
+                del L[key]
+                self._write_lora(L, sd[f"lora_layers.{i}.lora_A"], sd[f"lora_layers.{i}.lora_B"])
             layers.append(L)
         pk["layers"] = layers
+        pk["zero64"] = torch.zeros(_LORA_PAD, device=dev)
         pk["lnw"], pk["lnb"] = f32(sd["backbone.layernorm.weight"]), f32(sd["backbone.layernorm.bias"])
         focal = []
         for i in range(self.cfg.num_iterations):
@@ -378,8 +426,11 @@ class CognitiveAimModel(nn.Module):
             fl = dict(device=dev, dtype=torch.float32)
             ws = {
                 "patches": torch.empty(B * N, ops.PATCH_ROW_STRIDE, **bf),
-                "x": torch.empty(B * T, _D, **fl), "h": torch.empty(B * T, _D, **bf),
-                "qkv": torch.empty(B * T, 3 * _D, **bf), "att": torch.empty(B * T, _D, **bf),
+                "x": torch.empty(B * T, _D, **fl),
+                # with lora_mode: fused the rows of the adapted projection's input carry 64 extra columns (t = h A^T)
+                "h_ext": torch.empty(B * T, _D + (_LORA_PAD if self._lora_fused() and self.cfg.lora_merge_target != "attention_output" else 0), **bf),
+                "att_ext": torch.empty(B * T, _D + (_LORA_PAD if self._lora_fused() and self.cfg.lora_merge_target == "attention_output" else 0), **bf),
+                "qkv": torch.empty(B * T, 3 * _D, **bf),
                 "mlp": torch.empty(B * T, _MLP, **bf), "tokens": torch.empty(B, T, _D, **fl),
                 "xin": torch.empty(B * N, _D, **bf), "qk": torch.empty(B * N, 2 * _D, **bf),
                 "pm": torch.empty(B, N, P, **fl), "ps": torch.empty(B, N, P, **fl), "pc": torch.empty(B, P, N, **fl),
@@ -408,6 +459,7 @@ class CognitiveAimModel(nn.Module):
                 "att_run": torch.empty(_MAX_CURIOSITY_RUNS, B, N, **fl),
                 "graphs": {},
             }
+            ws["h"], ws["att"] = ws["h_ext"][:, :_D], ws["att_ext"][:, :_D]
             if os.environ.get("CA_POISON_WS", "0") not in ("", "0"):
                 # test aid: every floating-point workspace starts as NaN, so a kernel that reads a slot nobody wrote
                 # (e.g. an unwritten partial-sum column) produces NaN instead of plausible stale data
@@ -513,11 +565,21 @@ class CognitiveAimModel(nn.Module):
         x, h = ws["x"], ws["h"]
         ops.cls_rows(x, pk["cls"], tb["pos"], B, T, _D)
         ops.gemm(patches, pk["patch_w"], ops.EPI_PATCH_F32, x, bias=pk["patch_b"], pos=tb["pos"], patches_per_img=N)
+        fused = self._lora_fused()
+        on_out = fused and self.cfg.lora_merge_target == "attention_output"
         for L in pk["layers"]:
             ops.layernorm(x, L["n1w"], L["n1b"], h)
-            ops.gemm(h, L["wqkv"], ops.EPI_BIAS_BF16, ws["qkv"], bias=L["bqkv"])
+            if fused and not on_out:
+                ops.gemm(h, L["lora_a"], ops.EPI_BIAS_BF16, ws["h_ext"][:, _D:], bias=pk["zero64"])  # t = h A^T
+                ops.gemm(ws["h_ext"], L["wqkv_ext"], ops.EPI_BIAS_BF16, ws["qkv"], bias=L["bqkv"])
+            else:
+                ops.gemm(h, L["wqkv"], ops.EPI_BIAS_BF16, ws["qkv"], bias=L["bqkv"])
             ops.attention(ws["qkv"], ws["att"], B, T, _HEADS)
-            ops.gemm(ws["att"], L["wo"], ops.EPI_RESID_F32, x, bias=L["bo"], ls=L["ls1"])
+            if on_out:
+                ops.gemm(ws["att"], L["lora_a"], ops.EPI_BIAS_BF16, ws["att_ext"][:, _D:], bias=pk["zero64"])
+                ops.gemm(ws["att_ext"], L["wo_ext"], ops.EPI_RESID_F32, x, bias=L["bo"], ls=L["ls1"])
+            else:
+                ops.gemm(ws["att"], L["wo"], ops.EPI_RESID_F32, x, bias=L["bo"], ls=L["ls1"])
             ops.layernorm(x, L["n2w"], L["n2b"], h)
             ops.gemm(h, L["w1"], ops.EPI_GELU_BF16, ws["mlp"], bias=L["b1"])
             ops.gemm(ws["mlp"], L["w2"], ops.EPI_RESID_F32, x, bias=L["b2"], ls=L["ls2"])

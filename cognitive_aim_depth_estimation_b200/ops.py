@@ -121,7 +121,11 @@ def attention(qkv, out, B, T, H):
     _req(qkv, torch.bfloat16, "qkv")
     _req(out, torch.bfloat16, "out")
     e0 = _begin()
-    check(_lib.load().ca_attention_bf16(ptr(qkv), ptr(out), B, T, H, stream_ptr()), "ca_attention_bf16")
+    if out.stride(-2) != H * 64:  # a strided view: the rows carry LoRA columns behind the H*64 outputs
+        check(_lib.load().ca_attention_bf16_ld(ptr(qkv), ptr(out), out.stride(-2), B, T, H, stream_ptr()),
+              "ca_attention_bf16_ld")
+    else:
+        check(_lib.load().ca_attention_bf16(ptr(qkv), ptr(out), B, T, H, stream_ptr()), "ca_attention_bf16")
     _end(e0, "attention", 1, 4.0 * B * H * T * T * 64)
     return out
 
@@ -159,8 +163,12 @@ def layernorm(x, gamma, beta, out, eps=1e-6):
     _req(x, torch.float32, "x")
     rows, D = x.numel() // x.shape[-1], x.shape[-1]
     e0 = _begin()
-    check(_lib.load().ca_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), int(out.dtype == torch.bfloat16), rows, D,
-                                   eps, stream_ptr()), "ca_layernorm")
+    if out.dim() >= 2 and out.stride(-2) != D:  # strided rows (LoRA columns behind each row)
+        check(_lib.load().ca_layernorm_ld(ptr(x), ptr(gamma), ptr(beta), ptr(out), int(out.dtype == torch.bfloat16),
+                                          out.stride(-2), rows, D, eps, stream_ptr()), "ca_layernorm_ld")
+    else:
+        check(_lib.load().ca_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), int(out.dtype == torch.bfloat16), rows,
+                                       D, eps, stream_ptr()), "ca_layernorm")
     _end(e0, "layernorm", 1, float(rows * D * (4 + out.element_size())))
     return out
 

@@ -64,6 +64,9 @@ int ca_gemm_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K, int 
 /* out[B*T, H*64] = softmax(Q K^T / 8) V per (image, head); qkv is the fused [B*T, 3*H*64] activation
  * (Q | K | V column blocks).  Replaces F.scaled_dot_product_attention at HF modeling_dinov2.py:215-229. */
 int ca_attention_bf16(const uint16_t* qkv, uint16_t* out, int B, int T, int H, void* stream);
+/* the same with an output row pitch of `ldo` elements (>= H*64): the output feeds a GEMM whose K dimension is extended by
+ * the LoRA columns stored behind each row (see ca_gemm_bf16 with K > 768 in model.py, `lora_mode: fused`). */
+int ca_attention_bf16_ld(const uint16_t* qkv, uint16_t* out, int ldo, int B, int T, int H, void* stream);
 
 /* Bandwidth-bound row kernels ------------------------------------------------------------------- */
 /* fp32 CHW images [B,3,S,S] (the tensor `forward` receives) -> bf16 patch rows [B*(S/14)^2, 592]
@@ -78,6 +81,9 @@ int ca_cls_rows(float* x, const float* cls, const float* pos, int B, int T, int 
 /* LayerNorm(D=768) of fp32 rows -> bf16 (out_is_bf16=1) or fp32.  HF modeling_dinov2.py:354,359,449. */
 int ca_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_is_bf16, int rows, int D,
                  float eps, void* stream);
+/* the same with an output row pitch of `ld_out` elements (>= D). */
+int ca_layernorm_ld(const float* x, const float* gamma, const float* beta, void* out, int out_is_bf16, int ld_out,
+                    int rows, int D, float eps, void* stream);
 /* xin[b,n,:] = bf16(tokens[b,1+n,:] * rowscale[b,n] + pe[n,:]); rowscale may be NULL (=1).
  * reference src/model.py:184 (PE add) and :426 (re-focus, folded into a per-row scale). */
 int ca_focal_input(const float* tokens, const float* pe, const float* rowscale, uint16_t* xin, int B, int N, int D,

@@ -181,26 +181,44 @@ def test_lora_adapters_are_ignored_like_the_reference(cuda_device):
     assert (h.cpu().numpy().argmax(-1) == gold["heat"].argmax(-1)).all()
 
 
-@pytest.mark.parametrize("target", ["query", "attention_output"])
-def test_lora_merge_target_applies_the_adapters(cuda_device, target):
+@pytest.mark.parametrize("mode", ["merge", "fused"])
+@pytest.mark.parametrize("target", ["query", "value", "attention_output"])
+def test_lora_merge_target_applies_the_adapters(cuda_device, target, mode):
     """The opt-in (non-reference) `lora_merge_target`: y = W x + (alpha / rank) B A x on the chosen 768 -> 768 projection
-    of every encoder layer, checked against a plain fp32 restatement (the oracle backbone with W + (16/16) B A)."""
+    of every encoder layer, checked against a plain fp32 restatement (the oracle backbone with W + (16/16) B A) — with the
+    adapters merged into the packed weight (`lora_mode: merge`, default) and as the fused low-rank update of the GEMM
+    (`lora_mode: fused`: t = x A^T written behind each activation row, [W | s B] with one extra K block)."""
     from cognitive_aim_depth_estimation_b200.model import create_model
     sd = _lora_sd(0.5)  # B A of the same size as the weight it adapts
-    name = {"query": "attention.attention.query.weight", "attention_output": "attention.output.dense.weight"}[target]
+    name = {"query": "attention.attention.query.weight", "value": "attention.attention.value.weight",
+            "attention_output": "attention.output.dense.weight"}[target]
     merged = dict(sd)
     for i in range(12):
         k = f"backbone.encoder.layer.{i}.{name}"
         merged[k] = sd[k] + sd[f"lora_layers.{i}.lora_B"] @ sd[f"lora_layers.{i}.lora_A"]
     x = orc.synthetic_images(2, 224)
     want, plain = orc.dinov2_tokens(merged, x), orc.dinov2_tokens(sd, x)
-    m = create_model(dict(CFG, use_lora=True, lora_merge_target=target), {"num_cameras": 71}, device=cuda_device)
+    m = create_model(dict(CFG, use_lora=True, lora_merge_target=target, lora_mode=mode), {"num_cameras": 71},
+                     device=cuda_device)
     m.load_state_dict(sd)
     tok = m.backbone_tokens(x.cuda()).cpu()
     rel = ((tok - want).norm() / want.norm()).item()
     moved = ((plain - want).norm() / want.norm()).item()
     assert rel < TOKEN_REL_FRO, rel
     assert moved > 3 * rel, (moved, rel)  # the adapters really changed the tokens
+    if mode == "fused":
+        # per-call adapters: zero adapters give the plain backbone, the original ones give `want` again — no re-pack of W,
+        # and through the already captured CUDA graph
+        zero = {i: (torch.zeros(16, 768), torch.zeros(768, 16)) for i in range(12)}
+        m.set_lora_adapters(zero)
+        tok0 = m.backbone_tokens(x.cuda()).cpu()
+        assert ((tok0 - plain).norm() / plain.norm()).item() < TOKEN_REL_FRO
+        m.set_lora_adapters({i: (sd[f"lora_layers.{i}.lora_A"], sd[f"lora_layers.{i}.lora_B"]) for i in range(12)})
+        tok1 = m.backbone_tokens(x.cuda()).cpu()
+        assert torch.equal(tok1, tok)
+    else:
+        with pytest.raises(ValueError):
+            m.set_lora_adapters({})
 
 
 def test_camera_idx_range_is_checked_on_the_device(cuda_device, sd, cases):
