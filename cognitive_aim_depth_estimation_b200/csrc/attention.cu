@@ -102,7 +102,13 @@ constexpr int kTraceBase = 2 * 1024;  // offset into the debug buffer (roles: 0 
 #else
 #define CTRL_WAIT(bar, parity) mbar_wait(bar, parity)
 #endif
-constexpr float kLazyLimit = 8.0f;  // the accumulator reference moves only when a row max grew by > 2^8
+// The softmax reference of a row is set kRefBias (log2 units) ABOVE the largest score seen when it is set, and only moves
+// again when a later score exceeds that maximum by more than 2^kRefBias (see the step function).
+constexpr float kRefBias = 64.0f;
+// CA_ATTN_EXACT_MAX=1 (compile time): every step computes its exact row maximum (the A/B control of the max-free step)
+#ifndef CA_ATTN_EXACT_MAX
+#define CA_ATTN_EXACT_MAX 0
+#endif
 
 struct AttnArgs {
   int T;          // tokens per image
@@ -399,37 +405,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
     float l_prev = 1.f;
     int k = 0;
     float m_acc = -INFINITY, l_run = 0.f;  // reference (log2 domain) O and l_run are expressed in; running row sum
-    uint32_t v[64];        // the S row of the current step (fp32 bits); may already hold the NEXT step's row (have_v)
-    bool have_v = false;
-    // One 64-key step.  kBoundary = step 0 of an item, which also carries the previous item's epilogue and the next
-    // item's Q tile; it is a separate instantiation so that the steady-state step stays lean.
-    auto step = [&](auto boundary_tag, const int i) {
-      constexpr bool boundary = decltype(boundary_tag)::value;
-      const int bb = g & 1;
-      const int valid = p.T - i * kSubK;  // >= 64 on every step but the last
-      const uint32_t t_s = t_lane + kTmemS + bb * kSubK;
-      uint32_t qv[boundary ? 32 : 1];
-      if constexpr (boundary) {
-        it_next = read_item(k + 1);
-        if (it_next >= 0) q_load(it_next, qv);  // in flight under this step's exponentials
-      }
-      uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-      uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-      if (warp == 2) TRACE(0, g, 0);
-      if (!have_v) {  // not prefetched at the end of the previous step
-        mbar_wait(&s_full[bb], (g >> 1) & 1);
-        tc_fence_after();
-        tmem_ld32(t_s, v0);
-        tmem_ld32(t_s + 32, v1);
-      }
-      if (warp == 2) TRACE(0, g, 1);
-      tmem_ld_wait();
-      if (valid < kSubK) {
-#pragma unroll
-        for (int c = 0; c < kSubK; ++c)
-          if (c >= valid) v[c] = 0xff800000u;  // -inf: exp2 -> 0, ignored by the max
-      }
-      // ---- exact row max, four independent chains ----
+    uint32_t v[64];        // the S row of the current step (fp32 bits)
+    // Row statistics the exact way: row maximum of the 64 scores in `v`, reference raised to it (plus the bias below) when
+    // it grew, running sum and — on a step that is not the first of its item — the O accumulator rescaled to the new
+    // reference.  Runs on the first step of every item and on the (rare) steps the fast path below hands back.
+    auto exact_reference = [&](const uint32_t (&v)[64], bool first_step, int bb) {
       float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]),
             m3 = __uint_as_float(v[3]);
 #pragma unroll
@@ -441,44 +421,35 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
           m3 = fmaxf(m3, fmaxf(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7])));
         }
       }
-#if CA_ATTN_ABLATE & 1   // timing experiment: no dependency of the exponentials on this step's maximum
-      const float tile_max = boundary ? fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale : m_acc;
-#else
       const float tile_max = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale;  // scale > 0
-#endif
-      // ---- lazy reference update (warp-uniform decision; always taken on the first step of an item) ----
-      if (__any_sync(0xffffffffu, tile_max > m_acc + kLazyLimit)) {
-        const float m_new = fmaxf(m_acc, tile_max);
-        const float alpha = fast_exp2(m_acc - m_new);  // 0 on the first step (m_acc = -inf)
-        l_run *= alpha;
-        m_acc = m_new;
-        if (!boundary) {
-          mbar_wait(&pv_done[bb ^ 1], ((g - 1) >> 1) & 1);  // P V of step g-1 (hence every earlier one) has finished
-          tc_fence_after();
+      const float m_new = fmaxf(m_acc, tile_max + kRefBias);
+      const float alpha = fast_exp2(m_acc - m_new);  // 0 on the first step (m_acc = -inf), 1 for rows that did not grow
+      l_run *= alpha;
+      m_acc = m_new;
+      if (!first_step) {
+        mbar_wait(&pv_done[bb ^ 1], ((g - 1) >> 1) & 1);  // P V of step g-1 (hence every earlier one) has finished
+        tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[16];
-            tmem_ld16(t_o + c * 16, o);
-            tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[16];
+          tmem_ld16(t_o + c * 16, o);
+          tmem_ld_wait();
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk) o[kk] = __float_as_uint(__uint_as_float(o[kk]) * alpha);
-            tmem_st16(t_o + c * 16, o);
-          }
+          for (int kk = 0; kk < 16; ++kk) o[kk] = __float_as_uint(__uint_as_float(o[kk]) * alpha);
+          tmem_st16(t_o + c * 16, o);
         }
       }
-      // ---- P = exp2(s * scale - m_acc) -> bf16x2 -> TMEM (over the S columns just read) ; fp32 row sum ----
+    };
+    // P = exp2(s * scale - m_acc) -> bf16x2 in pk; returns the fp32 row sum of the step
+    auto exponentials = [&](const uint32_t (&v)[64], uint32_t (&pk)[32]) -> float {
       const float neg_m = -m_acc;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      uint32_t pk[32];
 #pragma unroll
       for (int t = 0; t < kSubK / 8; ++t) {
         float e[8];
 #pragma unroll
         for (int kk = 0; kk < 8; kk += 2) {
           ffma2(e[kk], e[kk + 1], __uint_as_float(v[8 * t + kk]), __uint_as_float(v[8 * t + kk + 1]), scale, neg_m);
-#if CA_ATTN_ABLATE & 2   // timing experiment: no exponentials at all
-          if (!boundary) continue;
-#endif
           if (kk >= 8 - 2 * static_cast<int>((kPolyMask >> (2 * t)) & 3u)) {  // compile-time split MUFU / polynomial
             exp2_poly2(e[kk], e[kk + 1]);
           } else {
@@ -495,9 +466,70 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
         pk[4 * t + 2] = pack_bf16x2(e[4], e[5]);
         pk[4 * t + 3] = pack_bf16x2(e[6], e[7]);
       }
+      return (s0 + s1) + (s2 + s3);
+    };
+    // One 64-key step.  kBoundary = step 0 of an item, which also carries the previous item's epilogue and the next
+    // item's Q tile; it is a separate instantiation so that the steady-state step stays lean.
+    //
+    // The steady-state step computes NO row maximum: the exponentials use the reference the row already has, which sits
+    // kRefBias = 64 (log2 units) above the largest score seen when it was set, so P = 2^(s - ref) stays below 1 as long as
+    // no score exceeds that maximum by more than 2^64 — and floating point does not care where in its range P, the row
+    // sum and O live (the final O / l cancels the reference).  A score that does break out shows up as a P >= 2 (exponent
+    // MSB of the packed bf16) or as a wrapped / negative polynomial result (sign bit): one OR-reduction of the 32 packed
+    // words finds either, and the warp then redoes the step the exact way (re-reading S, which P has not overwritten
+    // yet).  This takes the 31 max instructions, the vote on the maximum and — more important — the dependency of every
+    // exponential on the row maximum off the step.
+    auto step = [&](auto boundary_tag, const int i) {
+      constexpr bool boundary = decltype(boundary_tag)::value;
+      const int bb = g & 1;
+      const int valid = p.T - i * kSubK;  // >= 64 on every step but the last
+      const uint32_t t_s = t_lane + kTmemS + bb * kSubK;
+      uint32_t qv[boundary ? 32 : 1];
+      if constexpr (boundary) {
+        it_next = read_item(k + 1);
+        if (it_next >= 0) q_load(it_next, qv);  // in flight under this step's exponentials
+      }
+      uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+      uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+      auto load_row = [&]() {
+        tmem_ld32(t_s, v0);
+        tmem_ld32(t_s + 32, v1);
+        tmem_ld_wait();
+        if (valid < kSubK) {
+#pragma unroll
+          for (int c = 0; c < kSubK; ++c)
+            if (c >= valid) v[c] = 0xff800000u;  // -inf: exp2 -> 0, ignored by the max
+        }
+      };
+      if (warp == 2) TRACE(0, g, 0);
+      mbar_wait(&s_full[bb], (g >> 1) & 1);
+      tc_fence_after();
+      if (warp == 2) TRACE(0, g, 1);
+      load_row();
+      uint32_t pk[32];
+      float step_sum;
+      if constexpr (boundary) {
+        exact_reference(v, true, bb);
+        step_sum = exponentials(v, pk);
+      } else {
+#if CA_ATTN_EXACT_MAX
+        exact_reference(v, false, bb);
+        step_sum = exponentials(v, pk);
+#else
+        step_sum = exponentials(v, pk);
+        uint32_t any = 0;
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) any |= pk[c] | pk[c + 1];
+        if (__any_sync(0xffffffffu, (any & 0xC000C000u) != 0u)) {  // some P >= 2, negative or NaN: the reference is stale
+          load_row();
+          exact_reference(v, false, bb);
+          step_sum = exponentials(v, pk);
+        }
+#endif
+      }
       if (warp == 2) TRACE(0, g, 2);
       tmem_st32(t_s, pk);
-      l_run += (s0 + s1) + (s2 + s3);
+      l_run += step_sum;
       if constexpr (boundary) {
         // the previous item's last P V has long finished: read its O out before this step's P V may overwrite it
         if (k > 0) epilogue(k - 1, it_prev, l_prev);
@@ -511,17 +543,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
           if (lane == 0) mbar_arrive(&q_ready[(k + 1) & 1]);
         }
       }
-      // S of the next step of this item (issued two steps ago, normally long complete) starts its way into registers now,
-      // under the store wait / fence / hand-over of this step, instead of after them.
-      have_v = false;
-#if CA_ATTN_PREFETCH
-      if (i + 1 < n_sub && __all_sync(0xffffffffu, mbar_try_wait(&s_full[bb ^ 1], ((g + 1) >> 1) & 1))) {
-        tc_fence_after();
-        tmem_ld32(t_lane + kTmemS + (bb ^ 1) * kSubK, v0);
-        tmem_ld32(t_lane + kTmemS + (bb ^ 1) * kSubK + 32, v1);
-        have_v = true;
-      }
-#endif
       tmem_st_wait();     // P (and a rescaled O) are in TMEM
       tc_fence_before();
       __syncwarp();
