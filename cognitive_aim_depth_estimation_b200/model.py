@@ -111,6 +111,23 @@ def _param_specs(cfg: EffectiveConfig):
     return s
 
 
+_NVTX = os.environ.get("CA_NVTX", "0") not in ("", "0")
+
+
+@contextlib.contextmanager
+def _nvtx(name: str):
+    """Named NVTX range around a stage of the forward (CA_NVTX=1; visible in eager launches and at graph capture, e.g.
+    under `nsys` / `ncu --nvtx`).  The reference has no tracing hooks at all."""
+    if not _NVTX:
+        yield
+        return
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
+
+
 def _on_own_device(fn):
     """Run a public entry point with the model's GPU as the current CUDA device: every ca_* launch goes to the CURRENT
     device and torch.cuda.current_stream() is per device, so a model living on cuda:1 must not launch on cuda:0 just
@@ -152,8 +169,11 @@ class CognitiveAimModel(nn.Module):
             raise NotImplementedError(
                 "the B200 path is built for the configuration every shipped YAML resolves to "
                 "(ambient_stream + iterative_focal_stream [+ exif_prior_database]); got cognitive_modules without them")
-        if cfg.num_iterations > 8:
-            raise NotImplementedError("at most 8 focal iterations are built")
+        if not 1 <= cfg.num_iterations <= 4:
+            raise NotImplementedError("1..4 focal iterations are built (focal_value / focal_fusion kernels, csrc/heads.cu)")
+        if cfg.focal_hidden_dim != 256:
+            raise NotImplementedError("focal_hidden_dim must be 256 (the 768 -> 256 -> 64 focal projection is what the "
+                                      "kernels instantiate; every shipped YAML resolves to it)")
         # attributes demo.py reads (demo.py:71-73,380-382)
         self.backbone_size = cfg.backbone_size
         self.feature_dim = cfg.feature_dim
@@ -541,7 +561,9 @@ class CognitiveAimModel(nn.Module):
     @_on_own_device
     def backbone_tokens(self, images: torch.Tensor, *, patches: Optional[torch.Tensor] = None, B=None, S=None):
         """DINOv2 ViT-B/14 `last_hidden_state` [B, 1+N, 768] fp32 (HF modeling_dinov2.py:459-485).
-        `patches` (bf16 [B*N, 592] from `preprocess_u8`) may be given instead of images."""
+        `patches` (bf16 [B*N, 592] from `preprocess_u8`) may be given instead of images.
+        The result is a BORROWED view of the (B, S) workspace: the next call at the same shape overwrites it — clone it to
+        keep it (the forward passes return fresh tensors)."""
         pk = self._pack()
         dev = self._device()
         if patches is None:
@@ -563,11 +585,13 @@ class CognitiveAimModel(nn.Module):
         N, T = g * g, g * g + 1
         tb = self._tables[g]
         x, h = ws["x"], ws["h"]
-        ops.cls_rows(x, pk["cls"], tb["pos"], B, T, _D)
-        ops.gemm(patches, pk["patch_w"], ops.EPI_PATCH_F32, x, bias=pk["patch_b"], pos=tb["pos"], patches_per_img=N)
+        with _nvtx("cogaim.embeddings"):
+            ops.cls_rows(x, pk["cls"], tb["pos"], B, T, _D)
+            ops.gemm(patches, pk["patch_w"], ops.EPI_PATCH_F32, x, bias=pk["patch_b"], pos=tb["pos"], patches_per_img=N)
         fused = self._lora_fused()
         on_out = fused and self.cfg.lora_merge_target == "attention_output"
-        for L in pk["layers"]:
+        for li, L in enumerate(pk["layers"]):
+          with _nvtx(f"cogaim.layer{li}"):
             ops.layernorm(x, L["n1w"], L["n1b"], h)
             if fused and not on_out:
                 ops.gemm(h, L["lora_a"], ops.EPI_BIAS_BF16, ws["h_ext"][:, _D:], bias=pk["zero64"])  # t = h A^T
@@ -583,7 +607,8 @@ class CognitiveAimModel(nn.Module):
             ops.layernorm(x, L["n2w"], L["n2b"], h)
             ops.gemm(h, L["w1"], ops.EPI_GELU_BF16, ws["mlp"], bias=L["b1"])
             ops.gemm(ws["mlp"], L["w2"], ops.EPI_RESID_F32, x, bias=L["b2"], ls=L["ls2"])
-        ops.layernorm(x, pk["lnw"], pk["lnb"], ws["tokens"].view(B * T, _D))
+        with _nvtx("cogaim.final_norm"):
+            ops.layernorm(x, pk["lnw"], pk["lnb"], ws["tokens"].view(B * T, _D))
         return ws["tokens"]
 
     def _run(self, ws, key, fn):
@@ -622,6 +647,7 @@ class CognitiveAimModel(nn.Module):
         q, k = qk[:, :_D], qk[:, _D:]
         rs = None
         for i in range(iters):
+          with _nvtx(f"cogaim.focal{i}"):
             F_ = pk["focal"][i]
             ops.focal_input(ws["tokens"], tb["pe"], rs, ws["xin"], B, N, _D)
             ops.gemm(ws["xin"], F_["wqk"], ops.EPI_BIAS_BF16, qk, bias=F_["bqk"])
