@@ -122,7 +122,8 @@ struct AttnArgs {
   __nv_bfloat16* out;  // [B*T, H*64]
   int ldo;
   int stagger;     // cycles the second CTA of each SM waits before its first step
-  int* counter;    // global work counter of THIS launch (zeroed on the launch stream just before the kernel)
+  int* counter;    // [0] work counter, [1] CTAs that have finished — THIS launch's own slot of a ring of such pairs, zero when
+                   // the launch starts; the last CTA to leave zeroes it again for the launch that reuses the slot
   long long* dbg;  // CA_ATTN_DEBUG=1: per-CTA {cycles, smid}
 };
 
@@ -193,6 +194,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_sync();  // PDL: everything above is CTA-local; the QKV activation (and the work counter) are touched below
   const uint32_t tmem_base = *tmem_slot;
 
   // k-th item of this CTA (blocks until the scheduler has published it); -1 = the CTA has run out of work
@@ -565,6 +567,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    // re-arm this launch's counter slot (every claim of the launch has returned by now: a CTA only gets here after its
+    // scheduler drew the out-of-work sentinel).  No memset node between kernels: it would break the PDL chain.
+    __threadfence();
+    if (atomicAdd(p.counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+      p.counter[0] = 0;
+      p.counter[1] = 0;
+      __threadfence();
+    }
+  }
   if (p.dbg && threadIdx.x == 0) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -605,7 +617,9 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
     if (!st.ring) {
       CA_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
       CA_CUDA(cudaDeviceGetAttribute(&st.sms, cudaDevAttrMultiProcessorCount, dev));
-      CA_CUDA(cudaMalloc(&st.ring, kCounterRing * sizeof(int)));
+      CA_CUDA(cudaMalloc(&st.ring, 2 * kCounterRing * sizeof(int)));
+      CA_CUDA(cudaMemset(st.ring, 0, 2 * kCounterRing * sizeof(int)));
+      CA_CUDA(cudaDeviceSynchronize());  // (first use only: the zeroes must be in place whatever stream launches first)
     }
   }
   AttnArgs a;
@@ -621,11 +635,12 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
   a.ldo = ldo > 0 ? ldo : H * kHeadDim;
   CA_REQUIRE(a.ldo >= H * kHeadDim && a.ldo % 8 == 0, "attention: output leading dimension must be >= H*64 and a multiple of 8");
   const int grid = a.n_items < 2 * st.sms ? a.n_items : 2 * st.sms;  // persistent: two CTAs per SM
-  // Every launch owns one slot of a per-device ring of work counters, zeroed on ITS stream right before the kernel (a
-  // memset node when the launch is captured into a graph): launches that overlap on different streams never share a
-  // counter, and a launch that died leaves nothing behind for the next one.
-  a.counter = st.ring + (st.next.fetch_add(1u) % kCounterRing);
-  CA_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), stream));
+  // Every launch owns one slot of a per-device ring of 1024 (work counter, exit counter) pairs: launches that overlap on
+  // different streams never share a counter.  A slot is zero when its launch starts (zeroed at allocation, re-zeroed by
+  // the last CTA of the launch that used it 1024 launches earlier) — no memset node sits between the kernels of a
+  // captured forward, so the programmatic dependency chain from the QKV GEMM to this kernel stays intact.  (A launch
+  // that faults leaves its slot dirty; a faulted context is unusable anyway.)
+  a.counter = st.ring + 2 * (st.next.fetch_add(1u) % kCounterRing);
   static const int stagger = getenv("CA_ATTN_STAGGER") ? atoi(getenv("CA_ATTN_STAGGER")) : 0;
   a.stagger = stagger;
   static const bool want_dbg = getenv("CA_ATTN_DEBUG") != nullptr;
@@ -638,7 +653,7 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
     }
     a.dbg = d_dbg;
   }
-  attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tm_kv, a);
+  CA_TRY(launch_kernel(attention_fwd_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmemBytes, stream, tm_kv, a));
   CA_CUDA(cudaGetLastError());
   if (want_dbg) {
     static int calls = 0;

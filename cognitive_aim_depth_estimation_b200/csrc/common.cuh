@@ -67,6 +67,18 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the forward calls griddep_sync() before it touches global memory
+// a predecessor may have written: launched with the programmatic-serialisation attribute (host.h: launch_kernel) its CTAs
+// may become resident and run their prologue (barrier init, TMEM allocation, descriptor prefetch) while the previous
+// kernel of the stream drains, and block here until that kernel has completed and flushed; launched normally both
+// instructions are no-ops.  launch_dependents comes first so that the NEXT kernel's launch overlaps this one as well.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2): half the issue slots of the scalar forms
 // ---------------------------------------------------------------------------------------------
 // d = a * s + c with scalar s, c broadcast to both lanes

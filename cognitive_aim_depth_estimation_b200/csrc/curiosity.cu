@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(kHeadsThreads) curiosity_kernel(const Curiosit
                                                                   const float* __restrict__ noise,
                                                                   float* __restrict__ reward_raw,
                                                                   float* __restrict__ reward) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   __shared__ __align__(16) float s_cls[768];
   __shared__ __align__(16) float s_h[768];
   __shared__ __align__(16) float s_mu[192];
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(kHeadsThreads) curiosity_kernel(const Curiosit
 // The reference walks the batch in order: history[ptr] = reward; ptr = (ptr + 1) % len   (src/model.py:770-773)
 __global__ void history_update_kernel(const float* __restrict__ reward_raw, int B, float* __restrict__ history, int len,
                                       long long* __restrict__ pointer) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   long long p = *pointer;
   for (int b = 0; b < B; ++b) {
@@ -125,6 +127,7 @@ __global__ void history_update_kernel(const float* __restrict__ reward_raw, int 
 __global__ void curiosity_modulation_kernel(const CuriosityModWeights wt, const float* __restrict__ reward, float lo,
                                             float hi, float* __restrict__ cur_weight, int B, int n_iters,
                                             int mod_hidden) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float s = reward[b];
@@ -166,7 +169,7 @@ int curiosity_modulation_launch(const CuriosityModWeights& w, const float* rewar
   CA_REQUIRE(w.amp_w0 && w.amp_b0 && w.amp_w1 && w.amp_b1, "curiosity_modulation: null amplifier weights");
   for (int i = 0; i < n_iters; ++i)
     CA_REQUIRE(w.mod_w0[i] && w.mod_b0[i] && w.mod_w1[i] && w.mod_b1[i], "curiosity_modulation: null modulator weights");
-  curiosity_modulation_kernel<<<(B + 127) / 128, 128, 0, stream>>>(w, reward, lo, hi, cur_weight, B, n_iters, mod_hidden);
+  CA_TRY(launch_kernel(curiosity_modulation_kernel, dim3((B + 127) / 128), dim3(128), 0, stream, w, reward, lo, hi, cur_weight, B, n_iters, mod_hidden));
   CA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -177,11 +180,11 @@ int curiosity_launch(const CuriosityWeights& w, const float* tokens, int tokens_
   CA_REQUIRE(tokens && eps && reward_raw && reward, "curiosity: null pointer");
   CA_REQUIRE(w.loc_w0 == nullptr || noise != nullptr, "curiosity: the hierarchical path needs the noise draw");
   CA_REQUIRE(B > 0, "curiosity: empty batch");
-  curiosity_kernel<<<B, kHeadsThreads, 0, stream>>>(w, tokens, tokens_per_img, eps, noise, reward_raw, reward);
+  CA_TRY(launch_kernel(curiosity_kernel, dim3(B), dim3(kHeadsThreads), 0, stream, w, tokens, tokens_per_img, eps, noise, reward_raw, reward));
   CA_CUDA(cudaGetLastError());
   if (history != nullptr && w.loc_w0 != nullptr) {  // the reference only records in the hierarchical branch (:683-685)
     CA_REQUIRE(pointer != nullptr && history_len > 0, "curiosity: history without pointer");
-    history_update_kernel<<<1, 32, 0, stream>>>(reward_raw, B, history, history_len, pointer);
+    CA_TRY(launch_kernel(history_update_kernel, dim3(1), dim3(32), 0, stream, reward_raw, B, history, history_len, pointer));
     CA_CUDA(cudaGetLastError());
   }
   return 0;

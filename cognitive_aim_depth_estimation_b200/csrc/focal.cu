@@ -30,6 +30,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 __global__ void rowstats_merge_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
                                       const float* __restrict__ weight, float* __restrict__ rmax,
                                       float* __restrict__ rinv, float* __restrict__ wtab, int rows, int P) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const float* m = pm + static_cast<size_t>(r) * P;
@@ -53,6 +54,7 @@ __global__ void rowstats_merge_kernel(const float* __restrict__ pm, const float*
 __global__ void __launch_bounds__(192) colsum_e_kernel(const __half* __restrict__ E, int lde, long long e_batch_stride,
                                                         const float* __restrict__ wtab, float* __restrict__ pc, int N,
                                                         int P) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   const int b = blockIdx.z;
   const int p = blockIdx.y;
   const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(256) focal_finalize_kernel(const float* __rest
                                                               float focus_strength, int mode,
                                                               const float* __restrict__ cur_weight,
                                                               float adaptive_weight) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   __shared__ float red[32];
   const int b = blockIdx.x;
   const float* pcb = pc + static_cast<size_t>(b) * P * N;
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(256) guided_softmax_kernel(const float* __rest
                                                               long long mask_batch_stride, float* __restrict__ heat,
                                                               int* __restrict__ argmax, int N, float alpha,
                                                               float temperature) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   __shared__ float red[32];
   __shared__ int redi[32];
   const int b = blockIdx.x;
@@ -205,6 +209,7 @@ __global__ void __launch_bounds__(192) weighted_pool_kernel(const float* __restr
                                                              int row_offset, const float* __restrict__ w,
                                                              const float* __restrict__ w2, float* __restrict__ partial,
                                                              int N, int D, int rows_per_split) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   const int b = blockIdx.y;
   const int split = blockIdx.x;
   const int n0 = split * rows_per_split;
@@ -242,7 +247,7 @@ int rowstats_merge_launch(const float* pm, const float* ps, const float* weight,
                           int rows, int P, cudaStream_t stream) {
   CA_REQUIRE(pm && ps, "rowstats_merge: null pointer");
   CA_REQUIRE((rmax && rinv) || wtab, "rowstats_merge: no output requested");
-  rowstats_merge_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(pm, ps, weight, rmax, rinv, wtab, rows, P);
+  CA_TRY(launch_kernel(rowstats_merge_kernel, dim3((rows + 255) / 256), dim3(256), 0, stream, pm, ps, weight, rmax, rinv, wtab, rows, P));
   CA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -254,7 +259,7 @@ int colsum_e_launch(const void* E, int lde, long long e_batch_stride, const floa
   CA_REQUIRE(P * 64 >= N && lde <= P * 64, "colsum_e: P row/column spans of 64 must cover N");
   CA_REQUIRE((reinterpret_cast<uintptr_t>(E) & 15) == 0 && e_batch_stride % 8 == 0, "colsum_e: E must be 16-byte aligned");
   dim3 grid((lde / 8 + 191) / 192, P, B);  // every partial slot is written (row spans past N contribute zeros)
-  colsum_e_kernel<<<grid, 192, 0, stream>>>(reinterpret_cast<const __half*>(E), lde, e_batch_stride, wtab, pc, N, P);
+  CA_TRY(launch_kernel(colsum_e_kernel, dim3(grid), dim3(192), 0, stream, reinterpret_cast<const __half*>(E), lde, e_batch_stride, wtab, pc, N, P));
   CA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -264,8 +269,8 @@ int focal_finalize_launch(const float* pc, const float* cbias, float* attn, cons
                           cudaStream_t stream) {
   CA_REQUIRE(pc && attn, "focal_finalize: null pointer");
   CA_REQUIRE(mode != 0 || cbias, "focal_finalize: null centre bias");
-  focal_finalize_kernel<<<B, 256, 0, stream>>>(pc, cbias, attn, rs_in, rs_out, N, P, focus_strength, mode,
-                                                  cur_weight, adaptive_weight);
+  CA_TRY(launch_kernel(focal_finalize_kernel, dim3(B), dim3(256), 0, stream, pc, cbias, attn, rs_in, rs_out, N, P, focus_strength, mode,
+                                                  cur_weight, adaptive_weight));
   CA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -274,7 +279,7 @@ int guided_softmax_launch(const float* base, const float* mask, long long mask_b
                           int B, int N, float alpha, float temperature, cudaStream_t stream) {
   CA_REQUIRE(base && mask && heat, "guided_softmax: null pointer");
   CA_REQUIRE(mask_batch_stride == 0 || mask_batch_stride >= N, "guided_softmax: mask batch stride must be 0 or >= N");
-  guided_softmax_kernel<<<B, 256, 0, stream>>>(base, mask, mask_batch_stride, heat, argmax, N, alpha, temperature);
+  CA_TRY(launch_kernel(guided_softmax_kernel, dim3(B), dim3(256), 0, stream, base, mask, mask_batch_stride, heat, argmax, N, alpha, temperature));
   CA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -285,7 +290,7 @@ int weighted_pool_launch(const float* src, long long src_batch_stride, int row_o
   CA_REQUIRE(D == 768, "weighted_pool: only D = 768 is instantiated");
   CA_REQUIRE(splits > 0, "weighted_pool: splits must be positive");
   const int rps = (N + splits - 1) / splits;
-  weighted_pool_kernel<<<dim3(splits, B), 192, 0, stream>>>(src, src_batch_stride, row_offset, w, w2, partial, N, D, rps);
+  CA_TRY(launch_kernel(weighted_pool_kernel, dim3(dim3(splits, B)), dim3(192), 0, stream, src, src_batch_stride, row_offset, w, w2, partial, N, D, rps));
   CA_CUDA(cudaGetLastError());
   return 0;
 }

@@ -362,6 +362,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_sync();  // PDL: barriers, TMEM and descriptors are set up; from here on the kernel touches its operands
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -514,6 +515,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
+  griddep_sync();  // PDL: barriers, TMEM and descriptors are set up; from here on the kernel touches its operands
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -630,7 +632,7 @@ int launch_inst2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap
   }));
   const int max_clusters = sm_count() / 2;
   const int clusters = ka.total_tiles < max_clusters ? ka.total_tiles : max_clusters;
-  kern<<<2 * clusters, kGemmThreads, Gemm2Cfg::kSmemBytes, stream>>>(ta, tw, tx, ka);
+  CA_TRY(launch_kernel(kern, dim3(2 * clusters), dim3(kGemmThreads), Gemm2Cfg::kSmemBytes, stream, ta, tw, tx, ka));
   CA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -646,7 +648,7 @@ int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
     return 0;
   }));
   int grid = ka.total_tiles < sm_count() ? ka.total_tiles : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, tx, ka);
+  CA_TRY(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tw, tx, ka));
   CA_CUDA(cudaGetLastError());
   return 0;
 }

@@ -15,6 +15,7 @@ namespace {
 __global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const HeadsWeights wt, const HeadsInputs in,
                                                               float* __restrict__ depth, float* __restrict__ conf,
                                                               float* __restrict__ fused_out) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   __shared__ __align__(16) float s_in[768];
   __shared__ __align__(16) float s_a[256];
   __shared__ __align__(16) float s_b[256];
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const HeadsWeights
 //   weighted = (sum_j c_j x~_j) Wv^T + bv   with  sum_j c_j = 1,   feat = projection(weighted)
 // pooled x~ arrives as split partials of (tokens*rowscale) plus split partials of the PE table.
 __global__ void __launch_bounds__(kHeadsThreads) focal_value_kernel(const FocalValueArgs a) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   __shared__ __align__(16) float s_x[768];
   __shared__ __align__(16) float s_v[768];
   __shared__ __align__(16) float s_h[256];
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(kHeadsThreads) focal_value_kernel(const FocalV
 __global__ void __launch_bounds__(kHeadsThreads) focal_fusion_kernel(const float* __restrict__ feats, int n_iters,
                                                                      const float* w0, const float* b0, const float* w1,
                                                                      const float* b1, float* __restrict__ out) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   __shared__ __align__(16) float s_in[256];
   __shared__ __align__(16) float s_h[128];
   __shared__ __align__(16) float s_o[64];
@@ -144,7 +147,7 @@ int heads_launch(const HeadsWeights& w, const HeadsInputs& in, float* depth, flo
   CA_REQUIRE(in.focal_feat || (in.pool_partial && in.tmp_w && in.tmp_b && in.pool_splits > 0),
              "heads: neither focal features nor pooled partials + projection given");
   CA_REQUIRE(in.exif == nullptr || in.camera_idx != nullptr, "heads: EXIF given without camera_idx");
-  heads_kernel<<<B, kHeadsThreads, 0, stream>>>(w, in, depth, conf, fused_out);
+  CA_TRY(launch_kernel(heads_kernel, dim3(B), dim3(kHeadsThreads), 0, stream, w, in, depth, conf, fused_out));
   CA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -152,7 +155,7 @@ int heads_launch(const HeadsWeights& w, const HeadsInputs& in, float* depth, flo
 int focal_value_launch(const FocalValueArgs& a, int B, cudaStream_t stream) {
   CA_REQUIRE(a.tok_partial && a.pe_partial && a.wv && a.bv && a.feat_out, "focal_value: null pointer");
   CA_REQUIRE(a.n_iters >= 1 && a.n_iters <= 4, "focal_value: 1..4 iterations supported");
-  focal_value_kernel<<<B, kHeadsThreads, 0, stream>>>(a);
+  CA_TRY(launch_kernel(focal_value_kernel, dim3(B), dim3(kHeadsThreads), 0, stream, a));
   CA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -161,7 +164,7 @@ int focal_fusion_launch(const float* feats, int n_iters, const float* w0, const 
                         const float* b1, float* out, int B, cudaStream_t stream) {
   CA_REQUIRE(feats && w0 && b0 && w1 && b1 && out, "focal_fusion: null pointer");
   CA_REQUIRE(n_iters >= 1 && n_iters <= 4, "focal_fusion: 1..4 iterations supported");
-  focal_fusion_kernel<<<B, kHeadsThreads, 0, stream>>>(feats, n_iters, w0, b0, w1, b1, out);
+  CA_TRY(launch_kernel(focal_fusion_kernel, dim3(B), dim3(kHeadsThreads), 0, stream, feats, n_iters, w0, b0, w1, b1, out));
   CA_CUDA(cudaGetLastError());
   return 0;
 }

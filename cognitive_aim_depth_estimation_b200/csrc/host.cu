@@ -3,6 +3,7 @@
 #include "host.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -105,6 +106,14 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t ro
   uint64_t strides[2] = {ld * 2, batch_stride * 2};
   uint32_t box[3] = {64, box_rows, 1};
   return make_tmap_bf16_sw128(out, base, 3, dims, strides, box);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CA_PDL");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  return on;
 }
 
 int current_device() {

@@ -46,6 +46,28 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t ro
 // residual epilogue's TMA reduce-add.
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
+// Kernel launch, optionally with the programmatic-dependent-launch attribute (CA_PDL=1 in the environment): the kernel
+// may then start while its predecessor on the stream drains; it synchronises with it through griddep_sync() (common.cuh).
+// OFF by default: measured on B200 (round 2, same box, alternating runs) the guided forward at 32 x 518^2 takes 12.70 ms
+// per step with it against 12.22 ms without, and a single image 1.39 ms either way — the early-resident CTAs of the
+// next kernel cost more than the launch latency they hide.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  CA_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  return 0;
+}
+
 int sm_count();         // SMs of the CURRENT device (cached per device)
 int current_device();   // cudaGetDevice, -1 on failure
 

@@ -100,6 +100,7 @@ __device__ __forceinline__ uint8_t clip8(int v) {
 __global__ void resize_h_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H0, int W0, int row0,
                                 int rows, int out_w, const int* __restrict__ xmin, const int* __restrict__ cnt,
                                 const int* __restrict__ kk, int ksize) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   const int xx = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
@@ -124,6 +125,7 @@ __global__ void resize_h_kernel(const uint8_t* __restrict__ src, uint8_t* __rest
 __global__ void resize_v_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int rows, int row0,
                                 int row_elems, const int* __restrict__ ymin, const int* __restrict__ cnt,
                                 const int* __restrict__ kk, int ksize, int out_h) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int yy = blockIdx.y;
   const int b = blockIdx.z;
@@ -162,16 +164,16 @@ int resize_u8_launch(const uint8_t* src, int B, int H0, int W0, int out_h, int o
     uint8_t* hdst = need_v ? tmp : out;
     CA_REQUIRE(hdst != nullptr, "resize: a two-pass resize needs the temporary buffer");
     dim3 grid((out_w + 127) / 128, rows, B);
-    resize_h_kernel<<<grid, 128, 0, stream>>>(src, hdst, H0, W0, row0, rows, out_w, th->d_xmin, th->d_cnt, th->d_kk,
-                                              th->ksize);
+    CA_TRY(launch_kernel(resize_h_kernel, dim3(grid), dim3(128), 0, stream, src, hdst, H0, W0, row0, rows, out_w, th->d_xmin, th->d_cnt, th->d_kk,
+                                              th->ksize));
     CA_CUDA(cudaGetLastError());
     vsrc = hdst;
   }
   if (need_v) {
     const int row_elems = out_w * 3;
     dim3 grid((row_elems + 255) / 256, out_h, B);
-    resize_v_kernel<<<grid, 256, 0, stream>>>(vsrc, out, rows, row0, row_elems, tv->d_xmin, tv->d_cnt, tv->d_kk,
-                                              tv->ksize, out_h);
+    CA_TRY(launch_kernel(resize_v_kernel, dim3(grid), dim3(256), 0, stream, vsrc, out, rows, row0, row_elems, tv->d_xmin, tv->d_cnt, tv->d_kk,
+                                              tv->ksize, out_h));
     CA_CUDA(cudaGetLastError());
   }
   return 0;

@@ -26,6 +26,7 @@ template <bool kU8>
 __global__ void __launch_bounds__(320) patch_rows_kernel(const void* __restrict__ img_v,
                                                           __nv_bfloat16* __restrict__ patches, int S, int g, float3 mean,
                                                           float3 inv_std) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   extern __shared__ __align__(16) uint8_t sm_all[];
   // uint8 path: the first 3 KB hold lut[c][v] = (v / 255 - mean_c) / std_c, the value ToTensor + Normalize give byte v of
   // channel c — one shared-memory read instead of an int->float conversion, an IEEE division and an FMA per element
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(320) patch_rows_kernel(const void* __restrict_
 // x[b, 0, :] = cls_token + pos[0, :]   (HF modeling_dinov2.py:108-112)
 __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos, int B,
                                 int T, int D) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
   const int b = i / D;
@@ -120,6 +122,7 @@ template <int D, typename OutT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, OutT* __restrict__ out, int rows,
                                                          float eps, int ld_out) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   constexpr int kVec = D / 128;  // float4 per lane
   const int row = blockIdx.x * (blockDim.x >> 5) + warp_id();
   if (row >= rows) return;
@@ -169,6 +172,7 @@ template <int D>
 __global__ void __launch_bounds__(256) focal_input_kernel(const float* __restrict__ tokens, const float* __restrict__ pe,
                                                            const float* __restrict__ rowscale,
                                                            __nv_bfloat16* __restrict__ xin, int B, int N) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   constexpr int kVec = D / 128;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp_id();
   if (row >= B * N) return;
@@ -201,7 +205,7 @@ static int patch_rows_launch(const void* images, __nv_bfloat16* patches, int B, 
     CA_CUDA(cudaFuncSetAttribute(patch_rows_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return 0;
   }));
-  patch_rows_kernel<kU8><<<dim3(g, B), 320, smem, stream>>>(images, patches, S, g, mean, inv_std);
+  CA_TRY(launch_kernel(patch_rows_kernel<kU8>, dim3(dim3(g, B)), dim3(320), smem, stream, images, patches, S, g, mean, inv_std));
   CA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -224,6 +228,7 @@ int preprocess_u8_launch(const uint8_t* images, __nv_bfloat16* patches, int B, i
 // (per-call projection, curiosity draws): a cudaMemcpyAsync would queue on the H2D copy engine behind whatever bulk
 // upload the application has in flight there (the next image batch, ~2 ms) and stall the compute stream for that long.
 __global__ void fetch_pinned_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
     dst[i] = src[i];
@@ -236,14 +241,14 @@ int fetch_pinned_launch(float* dst, const float* src_pinned_host, size_t n, cuda
   CA_CUDA(cudaPointerGetAttributes(&attr, src_pinned_host));
   CA_REQUIRE(attr.type == cudaMemoryTypeHost, "fetch_pinned: the source must be page-locked (pinned) host memory");
   const int grid = static_cast<int>((n + 255) / 256 < 64 ? (n + 255) / 256 : 64);
-  fetch_pinned_kernel<<<grid, 256, 0, stream>>>(dst, static_cast<const float*>(attr.devicePointer), n);
+  CA_TRY(launch_kernel(fetch_pinned_kernel, dim3(grid), dim3(256), 0, stream, dst, static_cast<const float*>(attr.devicePointer), n));
   CA_CUDA(cudaGetLastError());
   return 0;
 }
 
 int cls_rows_launch(float* x, const float* cls, const float* pos, int B, int T, int D, cudaStream_t stream) {
   CA_REQUIRE(x && cls && pos, "cls_rows: null pointer");
-  cls_rows_kernel<<<(B * D + 255) / 256, 256, 0, stream>>>(x, cls, pos, B, T, D);
+  CA_TRY(launch_kernel(cls_rows_kernel, dim3((B * D + 255) / 256), dim3(256), 0, stream, x, cls, pos, B, T, D));
   CA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -257,10 +262,10 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, void
   CA_REQUIRE(rows > 0, "layernorm: no rows");
   const int grid = (rows + 7) / 8;
   if (out_is_bf16)
-    layernorm_kernel<768, __nv_bfloat16><<<grid, 256, 0, stream>>>(x, gamma, beta, static_cast<__nv_bfloat16*>(out),
-                                                                   rows, eps, ld_out);
+    CA_TRY(launch_kernel(layernorm_kernel<768, __nv_bfloat16>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, static_cast<__nv_bfloat16*>(out),
+                                                                   rows, eps, ld_out));
   else
-    layernorm_kernel<768, float><<<grid, 256, 0, stream>>>(x, gamma, beta, static_cast<float*>(out), rows, eps, ld_out);
+    CA_TRY(launch_kernel(layernorm_kernel<768, float>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, static_cast<float*>(out), rows, eps, ld_out));
   CA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -270,7 +275,7 @@ int focal_input_launch(const float* tokens, const float* pe, const float* rowsca
   CA_REQUIRE(tokens && pe && xin, "focal_input: null pointer");
   CA_REQUIRE(D == 768, "focal_input: only D = 768 is instantiated");
   const int rows = B * N;
-  focal_input_kernel<768><<<(rows + 7) / 8, 256, 0, stream>>>(tokens, pe, rowscale, xin, B, N);
+  CA_TRY(launch_kernel(focal_input_kernel<768>, dim3((rows + 7) / 8), dim3(256), 0, stream, tokens, pe, rowscale, xin, B, N));
   CA_CUDA(cudaGetLastError());
   return 0;
 }

@@ -34,6 +34,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 
 __global__ void __launch_bounds__(kVisThreads) focus_normalize_kernel(const float* __restrict__ heat,
                                                                        float* __restrict__ norm, int N) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   extern __shared__ float a[];
   __shared__ float red[32];
   __shared__ float sel[2];
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(kVisThreads) focus_normalize_kernel(const floa
 
 // out[b, y, x] = order-1 zoom of norm[b] (g x g) to (H, W), scipy.ndimage.zoom semantics (grid_mode=False)
 __global__ void focus_zoom_kernel(const float* __restrict__ norm, float* __restrict__ out, int g, int H, int W) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
   const int b = blockIdx.z;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -115,13 +117,13 @@ int focus_map_launch(const float* heat, int B, int g, int out_h, int out_w, floa
     CA_CUDA(cudaFuncSetAttribute(focus_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4));
     return 0;
   }));
-  focus_normalize_kernel<<<B, kVisThreads, N * sizeof(float), stream>>>(heat, norm, N);
+  CA_TRY(launch_kernel(focus_normalize_kernel, dim3(B), dim3(kVisThreads), N * sizeof(float), stream, heat, norm, N));
   CA_CUDA(cudaGetLastError());
   if (out != nullptr) {
     CA_REQUIRE(out_h > 0 && out_w > 0, "focus_map: non-positive output size");
     dim3 block(32, 8);
     dim3 grid((out_w + 31) / 32, (out_h + 7) / 8, B);
-    focus_zoom_kernel<<<grid, block, 0, stream>>>(norm, out, g, out_h, out_w);
+    CA_TRY(launch_kernel(focus_zoom_kernel, dim3(grid), dim3(block), 0, stream, norm, out, g, out_h, out_w));
     CA_CUDA(cudaGetLastError());
   }
   return 0;
