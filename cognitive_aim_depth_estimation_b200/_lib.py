@@ -79,7 +79,7 @@ class ModelWeights(C.Structure):
                 ("focus_strength", C.c_float), ("focal", FocalWeights * 4), ("ffw0", C.c_void_p), ("ffb0", C.c_void_p),
                 ("ffw1", C.c_void_p), ("ffb1", C.c_void_p), ("heads", HeadsWeights), ("curiosity", CuriosityWeights),
                 ("exploration_history", C.c_void_p), ("history_len", C.c_int), ("history_pointer", C.c_void_p),
-                ("num_cameras", C.c_int)]
+                ("num_cameras", C.c_int), ("layernorm_folded", C.c_int)]
 
 
 class ForwardCall(C.Structure):
@@ -99,6 +99,9 @@ _SIGNATURES = {
     "ca_gemm_bf16": [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong,
                      C.c_longlong, C.c_int, c_ptr, C.c_int, C.c_longlong, c_ptr, c_ptr, c_ptr, C.c_int, C.c_float,
                      c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    "ca_gemm_bf16_ln": [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr,
+                        c_ptr, C.c_int, C.c_float, c_ptr, C.c_int, c_ptr],
+    "ca_ln_shadow": [c_ptr, c_ptr, C.c_int, c_ptr, C.c_int, C.c_int, c_ptr],
     "ca_attention_bf16": [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr],
     "ca_attention_bf16_ld": [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr],
     "ca_patchify_f32": [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr],

@@ -72,6 +72,46 @@ int ca_gemm_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K, int 
   return ca::gemm_launch(a, static_cast<cudaStream_t>(stream));
 }
 
+int ca_gemm_bf16_ln(const uint16_t* A, const uint16_t* W, int M, int N, int K, int lda, int ldw, int epilogue, void* out,
+                    int ldo, const float* bias, const float* ls, float* ln_stats, int ln_slots,
+                    float ln_eps, uint16_t* shadow, int ld_shadow, void* stream) {
+  if (epilogue != ca::EPI_LN_BIAS_BF16 && epilogue != ca::EPI_LN_GELU_BF16 && epilogue != ca::EPI_RESID_LN_F32)
+    return ca::invalid("ca_gemm_bf16_ln: epilogue must be one of CA_EPI_LN_BIAS_BF16, CA_EPI_LN_GELU_BF16, CA_EPI_RESID_LN_F32");
+  ca::GemmArgs a;
+  a.A = reinterpret_cast<const __nv_bfloat16*>(A);
+  a.W = reinterpret_cast<const __nv_bfloat16*>(W);
+  a.M = M;
+  a.N = N;
+  a.K = K;
+  a.lda = lda;
+  a.ldw = ldw;
+  a.batch = 1;
+  a.a_batch_stride = 0;
+  a.w_batch_stride = 0;
+  a.epilogue = epilogue;
+  a.out = out;
+  a.ldo = ldo;
+  a.out_batch_stride = 0;
+  a.bias = bias;
+  a.ls = ls;
+  a.pos = nullptr;
+  a.patches_per_img = 0;
+  a.scale_log2 = 0.f;
+  a.part_a = a.part_b = nullptr;
+  a.col_max = a.col_rinv = nullptr;
+  a.ln_stats = ln_stats;
+  a.ln_slots = ln_slots;
+  a.ln_eps = ln_eps;
+  a.shadow = reinterpret_cast<__nv_bfloat16*>(shadow);
+  a.ld_shadow = ld_shadow;
+  return ca::gemm_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+int ca_ln_shadow(const float* x, uint16_t* shadow, int ld_shadow, float* stats, int rows, int D, void* stream) {
+  return ca::ln_shadow_launch(x, reinterpret_cast<__nv_bfloat16*>(shadow), ld_shadow, stats, rows, D,
+                              static_cast<cudaStream_t>(stream));
+}
+
 int ca_attention_bf16(const uint16_t* qkv, uint16_t* out, int B, int T, int H, void* stream) {
   return ca::attention_launch(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), B, T,
                               H, static_cast<cudaStream_t>(stream));

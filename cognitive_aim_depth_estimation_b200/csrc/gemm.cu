@@ -7,7 +7,8 @@
 //                                  the whole warp allocates / frees TMEM
 //   warps 2..9  : epilogue       — tcgen05.ld from the warp's TMEM lane quadrant (warp_id % 4), two warps per
 //                                  quadrant split the BN columns; fused bias / GELU / LayerScale+residual /
-//                                  pos-embed / softmax-statistics epilogues straight to global memory
+//                                  pos-embed / softmax-statistics epilogues straight to global memory, and the
+//                                  LayerNorm-folding pair (gemm.cuh EPI_LN_* / EPI_RESID_LN_F32)
 //
 // Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 // Tiles are scheduled statically (tile = blockIdx.x + i * gridDim.x) with the N index fastest so the CTAs
@@ -70,6 +71,11 @@ struct GemmKernelArgs {
   const float* col_max;
   const float* col_rinv;
   int partials;
+  float2* ln_stats;        // EPI_LN_* (read) / EPI_RESID_LN_F32 (written): [M, ln_slots] (sum, M2) per 128-column span
+  int ln_slots;
+  float ln_eps;
+  __nv_bfloat16* shadow;   // EPI_RESID_LN_F32: bf16 copy of the updated rows
+  int ld_shadow;
   int dbg;  // CA_GEMM_DEBUG experiments (bit 0: skip B loads, bit 1: skip A loads) — results are then garbage
 };
 
@@ -94,10 +100,30 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   fmul2(x0, x1, x0, x1, phi0, phi1);
 }
 
+// 1 / sqrt(var + eps) of a residual row from the per-128-column (sum, M2) pairs the residual epilogue (or ca_ln_shadow) left
+// (Chan's combination); 1 for rows past M.
+__device__ __forceinline__ float ln_row_rstd(const GemmKernelArgs& p, int row) {
+  if (row >= p.M) return 1.f;
+  const float2* st = p.ln_stats + static_cast<size_t>(row) * p.ln_slots;
+  const float inv_dim = 1.f / (128.f * p.ln_slots);
+  float tot = 0.f, m2 = 0.f;
+  for (int i = 0; i < p.ln_slots; ++i) {
+    const float2 t = __ldg(st + i);
+    tot += t.x;
+    m2 += t.y;
+  }
+  const float mean = tot * inv_dim;
+  for (int i = 0; i < p.ln_slots; ++i) {
+    const float d = __ldg(st + i).x * (1.f / 128.f) - mean;
+    m2 = fmaf(128.f * d, d, m2);
+  }
+  return rsqrtf(m2 * inv_dim + p.ln_eps);
+}
+
 // One epilogue warp: rows [32*q, 32*q+32) of the tile (q = warp_id % 4), columns [col0, col0 + BN/2).
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUtensorMap* tmap_x, uint32_t tmem_acc, int b,
-                                              int mt, int nt, int quad, int half, uint8_t* stage) {
+                                              int mt, int nt, int quad, int half, uint8_t* stage, float rstd = 1.f) {
   constexpr int kSpan = BN / 2;
   const int lane = lane_id();
   const int row = mt * BM + quad * 32 + lane;           // row inside batch b
@@ -196,7 +222,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
     const int lrow = lane >> 3;  // row within a group of 4 (8 passes cover the warp's 32 rows)
     const int seg = lane & 7;    // 16-byte piece of the 128-byte chunk row
     const uint32_t stage_s = smem_u32(stage);  // explicit .shared accesses (LDS / STS instead of generic LD.E / ST.E)
-    if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16) {
+    if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_GELU_BF16) {
+      constexpr bool kLn = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_GELU_BF16);
+      constexpr bool kGelu = (EPI == EPI_GELU_BF16 || EPI == EPI_LN_GELU_BF16);
+      // LayerNorm folded into this GEMM: A holds the raw residual rows, W is gamma-scaled with every row CENTRED
+      // (sum_k W'[n,k] = 0), so the accumulator already is sum_k (x_k - mean) W'[n,k]; what is left for the epilogue is
+      // the row's 1/std (`rstd`, ln_row_rstd: fetched while the accumulator was still being computed).
 #pragma unroll 1
       for (int c = 0; c < kSpan; c += 64) {
         const int col = col_base + c;
@@ -213,12 +244,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const float4 t = __ldg(b4 + 2 * j + h);
-                a[4 * h + 0] = __uint_as_float(v[8 * j + 4 * h + 0]) + t.x;
-                a[4 * h + 1] = __uint_as_float(v[8 * j + 4 * h + 1]) + t.y;
-                a[4 * h + 2] = __uint_as_float(v[8 * j + 4 * h + 2]) + t.z;
-                a[4 * h + 3] = __uint_as_float(v[8 * j + 4 * h + 3]) + t.w;
+                if constexpr (kLn) {
+                  a[4 * h + 0] = fmaf(rstd, __uint_as_float(v[8 * j + 4 * h + 0]), t.x);
+                  a[4 * h + 1] = fmaf(rstd, __uint_as_float(v[8 * j + 4 * h + 1]), t.y);
+                  a[4 * h + 2] = fmaf(rstd, __uint_as_float(v[8 * j + 4 * h + 2]), t.z);
+                  a[4 * h + 3] = fmaf(rstd, __uint_as_float(v[8 * j + 4 * h + 3]), t.w);
+                } else {
+                  a[4 * h + 0] = __uint_as_float(v[8 * j + 4 * h + 0]) + t.x;
+                  a[4 * h + 1] = __uint_as_float(v[8 * j + 4 * h + 1]) + t.y;
+                  a[4 * h + 2] = __uint_as_float(v[8 * j + 4 * h + 2]) + t.z;
+                  a[4 * h + 3] = __uint_as_float(v[8 * j + 4 * h + 3]) + t.w;
+                }
               }
-              if constexpr (EPI == EPI_GELU_BF16) {
+              if constexpr (kGelu) {
 #pragma unroll
                 for (int i = 0; i < 8; i += 2) gelu_erf2(a[i], a[i + 1]);
               }
@@ -432,10 +470,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int rest = tile / p.n_tiles;
       const int mt = rest % p.m_tiles;
       const int b = rest / p.m_tiles;
+      float rstd = 1.f;
+      if constexpr (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_GELU_BF16) rstd = ln_row_rstd(p, mt * BM + quad * 32 + lane);
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       epilogue_tile<BN, EPI>(p, &tmap_x, tmem_base + static_cast<uint32_t>(acc * BN), b, mt, nt, quad, half,
-                             smem_stage + e * kEpiStageBytes);
+                             smem_stage + e * kEpiStageBytes, rstd);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -479,12 +519,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                      const __grid_constant__ CUtensorMap tmap_x, const GemmKernelArgs p) {
   using Cfg = Gemm2Cfg;
   constexpr int BN = Cfg::BN;
+  constexpr bool kResidLn = (EPI == EPI_RESID_LN_F32);
+  constexpr int n_stages = Cfg::kStages;
+  constexpr int staging_bytes = Cfg::kStagingBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint8_t* smem_stage = smem + Cfg::kStages * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + Cfg::kStagingBytes);
+  uint8_t* smem_b = smem + n_stages * Cfg::kABytes;
+  uint8_t* smem_stage = smem + n_stages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + staging_bytes);
   uint64_t* full_bar = bars;                        // [kStages] TMA (both CTAs) -> leader's MMA warp; leader's copy used
   uint64_t* empty_bar = bars + Cfg::kStages;        // [kStages] leader's MMA (multicast commit) -> each CTA's producer
   uint64_t* acc_full = bars + 2 * Cfg::kStages;     // [2] leader's MMA (multicast commit) -> each CTA's epilogue
@@ -501,7 +544,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -540,7 +583,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           if (lb)
             tma_load_3d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_w, leader_full, kb * BK, nt_l * BN + rank * (BN / 2),
                             p.w_batched ? b : 0);
-          if (++stage == Cfg::kStages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -568,7 +611,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             umma_bf16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit_2sm(&empty_bar[stage], 3);  // frees the stage in BOTH CTAs
-          if (++stage == Cfg::kStages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -584,15 +627,138 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const int half = e >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if constexpr (kResidLn) {
+      // x += ls * (acc + bias) with the OLD rows read into the SM, because the LayerNorm that follows needs the new
+      // values.  Plain loads and stores, no TMA and so no proxy fence (a fence waits for the warp's earlier global stores
+      // to be acknowledged — measured: that serialised every chunk behind the previous chunk's stores): each warp walks
+      // its 32-row x 32-column chunks (4 per tile) as ONE stream across tiles.  Per chunk the update ls * (acc + bias)
+      // goes from the accumulator's thread-per-row layout through the swizzled staging buffer into the layout global
+      // memory wants (8 lanes per 128-byte row segment, 4 rows per instruction); there the old values — loaded one
+      // chunk ahead into the registers the previous chunk has just released — are added, and the fp32 rows, their
+      // bf16 copy (the next GEMM's A operand) and the running (sum, sum of squares) of each row leave from registers.
+      const int lrow = lane >> 3, seg = lane & 7;
+      const uint32_t stage_s = smem_u32(smem_stage + e * kEpiStageBytes);
+      const int my_tiles = cluster_id < p.total_tiles ? (p.total_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
+      const int total_chunks = my_tiles * 4;
+      // (first column of this warp's 128-column span, first row of its 32 rows) of the i-th tile of this cluster
+      auto tile_origin = [&](int i, int& col0, int& row0, int& nt) {
+        const int tile = cluster_id + i * n_clusters;
+        nt = tile % p.n_tiles;
+        const int mt2 = (tile / p.n_tiles) % p.m_tiles;
+        col0 = nt * BN + half * 128;
+        row0 = (mt2 * 2 + static_cast<int>(rank)) * BM + quad * 32;
+      };
+      float* const xbase = reinterpret_cast<float*>(p.out);
+      float4 old[8];  // piece i: row lrow + 4 i of the chunk, columns seg * 4 .. + 3
+      int n_col0 = 0, n_row0 = 0, n_nt = 0;  // origin of the tile the load stream is in
+      auto load_piece = [&](int s, int i) {  // chunk s, piece i -> old[i]
+        const int row = n_row0 + lrow + 4 * i;
+        old[i] = row < p.M ? *reinterpret_cast<const float4*>(xbase + static_cast<size_t>(row) * p.ldo + n_col0 + (s & 3) * 32 + seg * 4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      if (total_chunks > 0) {
+        tile_origin(0, n_col0, n_row0, n_nt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) load_piece(0, i);
+      }
+      float rs[8], rq[8];
+      int col0 = 0, row0 = 0, nt = 0;
+      int pf_col0 = 0, pf_row0 = 0;
+      for (int s = 0; s < total_chunks; ++s) {
+        const int g = s & 3;
+        if (g == 0) {
+          tile_origin(s >> 2, col0, row0, nt);
+          int pf_nt;
+          tile_origin((s >> 2) + 1, pf_col0, pf_row0, pf_nt);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rs[i] = rq[i] = 0.f;
+          mbar_wait(&acc_full[acc], acc_phase);
+          tc_fence_after();
+        }
+        const int col = col0 + g * 32;
+        // the registers hold ONE chunk of old values in flight; the rows a tile further on start their way from HBM into
+        // the L2 now, so that load finds them there
+        if (s + 4 < total_chunks && pf_row0 + lane < p.M)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(xbase + static_cast<size_t>(pf_row0 + lane) * p.ldo + pf_col0 + g * 32));
+        uint32_t v[32];
+        tmem_ld32(tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quad * 32) << 16) +
+                      static_cast<uint32_t>(half * 128 + g * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+          const float4 l4 = __ldg(reinterpret_cast<const float4*>(p.ls + col) + j);
+          float4 d;
+          fadd2v(d.x, d.y, __uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]), t.x, t.y);
+          fadd2v(d.z, d.w, __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]), t.z, t.w);
+          fmul2(d.x, d.y, d.x, d.y, l4.x, l4.y);
+          fmul2(d.z, d.w, d.z, d.w, l4.z, l4.w);
+          sts128f(stage_s + epi_off(lane, j), d);
+        }
+        if (g == 3) {  // the accumulator has been read: hand it back before the global-memory half of the chunk
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa_cluster(smem_u32(&acc_empty[acc]), 0));
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        } else {
+          __syncwarp();
+        }
+        // origin of the chunk after this one (its old values replace this chunk's, piece by piece)
+        const bool more = s + 1 < total_chunks;
+        if (more && ((s + 1) & 3) == 0) tile_origin((s + 1) >> 2, n_col0, n_row0, n_nt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = lrow + 4 * i;
+          const int row = row0 + rr;
+          const float4 d = lds128f(stage_s + epi_off(rr, seg));
+          float4 n;
+          fadd2v(n.x, n.y, old[i].x, old[i].y, d.x, d.y);
+          fadd2v(n.z, n.w, old[i].z, old[i].w, d.z, d.w);
+          if (more) load_piece(s + 1, i);
+          if (row < p.M) {
+            *reinterpret_cast<float4*>(xbase + static_cast<size_t>(row) * p.ldo + col + seg * 4) = n;
+            *reinterpret_cast<uint2*>(p.shadow + static_cast<size_t>(row) * p.ld_shadow + col + seg * 4) =
+                make_uint2(pack_bf16x2(n.x, n.y), pack_bf16x2(n.z, n.w));
+          }
+          rs[i] += (n.x + n.y) + (n.z + n.w);
+          rq[i] = fmaf(n.x, n.x, fmaf(n.y, n.y, fmaf(n.z, n.z, fmaf(n.w, n.w, rq[i]))));
+        }
+        __syncwarp();  // the staging buffer is free for the next chunk
+        if (g == 3) {
+          // the 8 lanes of a row segment hold the pieces of one row: (sum, sum of squares) of its 128 columns
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
+              rq[i] += __shfl_xor_sync(0xffffffffu, rq[i], o);
+            }
+          }
+          if (seg == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = row0 + lrow + 4 * i;
+              // M2 about the span mean; the squares are taken about 0, which costs a relative 1e-7 (1 + mean^2 / var)
+              if (row < p.M)
+                p.ln_stats[static_cast<size_t>(row) * p.ln_slots + nt * 2 + half] =
+                    make_float2(rs[i], fmaxf(rq[i] - rs[i] * rs[i] * (1.f / 128.f), 0.f));
+            }
+          }
+        }
+      }
+    } else
     for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
       const int nt = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
       const int mt = (rest % p.m_tiles) * 2 + static_cast<int>(rank);  // this CTA's 128-row tile
       const int b = rest / p.m_tiles;
+      float rstd = 1.f;
+      if constexpr (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_GELU_BF16) rstd = ln_row_rstd(p, mt * BM + quad * 32 + lane);
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       epilogue_tile<BN, EPI>(p, &tmap_x, tmem_base + static_cast<uint32_t>(acc * BN), b, mt, nt, quad, half,
-                             smem_stage + e * kEpiStageBytes);
+                             smem_stage + e * kEpiStageBytes, rstd);
       tc_fence_before();
       __syncwarp();
 #if CA_GEMM_RELEASE_ARRIVE
@@ -625,6 +791,7 @@ template <int EPI>
 int launch_inst2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tx, const GemmKernelArgs& ka,
                  cudaStream_t stream) {
   auto kern = gemm2_tcgen05_kernel<EPI>;
+  const int smem = Gemm2Cfg::kSmemBytes;
   static PerDeviceOnce configured;  // per instantiation and per device (the opt-in is per context)
   CA_TRY(configured.run([&]() -> int {
     CA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::kSmemBytes));
@@ -632,7 +799,7 @@ int launch_inst2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap
   }));
   const int max_clusters = sm_count() / 2;
   const int clusters = ka.total_tiles < max_clusters ? ka.total_tiles : max_clusters;
-  CA_TRY(launch_kernel(kern, dim3(2 * clusters), dim3(kGemmThreads), Gemm2Cfg::kSmemBytes, stream, ta, tw, tx, ka));
+  CA_TRY(launch_kernel(kern, dim3(2 * clusters), dim3(kGemmThreads), smem, stream, ta, tw, tx, ka));
   CA_CUDA(cudaGetLastError());
   return 0;
 }
@@ -665,18 +832,27 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   // CA_GEMM_1CTA is set; the (test-only) column-sum recompute pass keeps the single-CTA 128 x 128 kernel, whose operand
   // traffic (256 B/clk of fill + reads against a 128 B/clk shared-memory port) caps it near half the tensor rate
   static const bool force_1cta = getenv("CA_GEMM_1CTA") != nullptr;
-  const bool pair = !force_1cta && a.epilogue != EPI_COLSUM;
+  const bool resid_ln = a.epilogue == EPI_RESID_LN_F32;
+  const bool ln_in = a.epilogue == EPI_LN_BIAS_BF16 || a.epilogue == EPI_LN_GELU_BF16;
+  const bool pair = (!force_1cta || resid_ln) && a.epilogue != EPI_COLSUM;
   const int bn = (stats && !pair) ? 128 : 256;
   if (!stats) {
     CA_REQUIRE(a.N % 32 == 0, "gemm: N must be a multiple of 32 for the dense epilogues");
-    CA_REQUIRE((a.epilogue != EPI_BIAS_BF16 && a.epilogue != EPI_GELU_BF16) || a.N % 64 == 0,
-               "gemm: the bf16 epilogues need N % 64 == 0");
+    const bool bf16_out = a.epilogue == EPI_BIAS_BF16 || a.epilogue == EPI_GELU_BF16 || ln_in;
+    CA_REQUIRE(!bf16_out || a.N % 64 == 0, "gemm: the bf16 epilogues need N % 64 == 0");
     CA_REQUIRE(a.out != nullptr, "gemm: null output");
     CA_REQUIRE(a.epilogue == EPI_F32 || a.bias != nullptr, "gemm: null bias");
-    const int vec = (a.epilogue == EPI_BIAS_BF16 || a.epilogue == EPI_GELU_BF16) ? 8 : 4;
+    const int vec = bf16_out ? 8 : 4;
     CA_REQUIRE(a.ldo % vec == 0, "gemm: ldo must keep rows 16-byte aligned");
-    CA_REQUIRE(a.epilogue != EPI_RESID_F32 || a.ls != nullptr, "gemm: null LayerScale");
-    CA_REQUIRE(a.epilogue != EPI_RESID_F32 || a.N % 256 == 0, "gemm: the residual epilogue needs N % 256 == 0");
+    const bool resid = a.epilogue == EPI_RESID_F32 || resid_ln;
+    CA_REQUIRE(!resid || a.ls != nullptr, "gemm: null LayerScale");
+    CA_REQUIRE(!resid || a.N % 256 == 0, "gemm: the residual epilogues need N % 256 == 0");
+    CA_REQUIRE(!(ln_in || resid_ln) || (a.ln_stats != nullptr && a.ln_slots > 0 && a.batch == 1),
+               "gemm: the LayerNorm-folding epilogues need a statistics buffer and are not batched");
+    CA_REQUIRE(!ln_in || (a.K == 128 * a.ln_slots && a.ln_eps > 0.f), "gemm: EPI_LN_* need K == 128 * ln_slots and eps > 0");
+    CA_REQUIRE(!resid_ln || (a.shadow != nullptr && a.N == 128 * a.ln_slots && a.ld_shadow % 8 == 0 &&
+                             (reinterpret_cast<uintptr_t>(a.shadow) & 15) == 0),
+               "gemm: EPI_RESID_LN_F32 needs a 16-byte aligned bf16 shadow and N == 128 * ln_slots");
     CA_REQUIRE(a.epilogue != EPI_PATCH_F32 || (a.pos != nullptr && a.patches_per_img > 0), "gemm: null pos-embed");
   } else {
     CA_REQUIRE(a.part_a != nullptr, "gemm: null partial buffer");
@@ -696,7 +872,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   CA_TRY(make_tmap_3d(&tw, a.W, wb ? a.batch : 1, a.N, a.K, a.ldw, wbs, pair ? bn / 2 : bn));
 
   CUtensorMap tx = ta;  // only the residual epilogue reads it
-  if (a.epilogue == EPI_RESID_F32) {
+  if (a.epilogue == EPI_RESID_F32 || resid_ln) {
     CA_REQUIRE(a.batch == 1, "gemm: the residual epilogue is not batched");
     CA_REQUIRE(a.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0, "gemm: residual rows must be 16-byte aligned");
     CA_TRY(make_tmap_f32_2d(&tx, a.out, a.M, a.N, a.ldo, 32));
@@ -724,6 +900,11 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   ka.col_max = a.col_max;
   ka.col_rinv = a.col_rinv;
   ka.partials = gemm_stats_partials(a.N);
+  ka.ln_stats = reinterpret_cast<float2*>(a.ln_stats);
+  ka.ln_slots = a.ln_slots;
+  ka.ln_eps = a.ln_eps;
+  ka.shadow = a.shadow;
+  ka.ld_shadow = a.ld_shadow;
   static const int dbg = getenv("CA_GEMM_DEBUG") ? atoi(getenv("CA_GEMM_DEBUG")) : 0;
   ka.dbg = dbg;
 
@@ -735,6 +916,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
       case EPI_PATCH_F32: return launch_inst2<EPI_PATCH_F32>(ta, tw, tx, ka, stream);
       case EPI_F32: return launch_inst2<EPI_F32>(ta, tw, tx, ka, stream);
       case EPI_ROWSTATS: return launch_inst2<EPI_ROWSTATS>(ta, tw, tx, ka, stream);
+      case EPI_LN_BIAS_BF16: return launch_inst2<EPI_LN_BIAS_BF16>(ta, tw, tx, ka, stream);
+      case EPI_LN_GELU_BF16: return launch_inst2<EPI_LN_GELU_BF16>(ta, tw, tx, ka, stream);
+      case EPI_RESID_LN_F32: return launch_inst2<EPI_RESID_LN_F32>(ta, tw, tx, ka, stream);
       default: return invalid("gemm: unknown epilogue");
     }
   }
@@ -744,6 +928,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     case EPI_RESID_F32: return launch_inst<256, EPI_RESID_F32>(ta, tw, tx, ka, stream);
     case EPI_PATCH_F32: return launch_inst<256, EPI_PATCH_F32>(ta, tw, tx, ka, stream);
     case EPI_F32: return launch_inst<256, EPI_F32>(ta, tw, tx, ka, stream);
+    case EPI_LN_BIAS_BF16: return launch_inst<256, EPI_LN_BIAS_BF16>(ta, tw, tx, ka, stream);
+    case EPI_LN_GELU_BF16: return launch_inst<256, EPI_LN_GELU_BF16>(ta, tw, tx, ka, stream);
     case EPI_ROWSTATS: return launch_inst<128, EPI_ROWSTATS>(ta, tw, tx, ka, stream);
     case EPI_COLSUM: return launch_inst<128, EPI_COLSUM>(ta, tw, tx, ka, stream);
     default: return invalid("gemm: unknown epilogue");

@@ -47,7 +47,7 @@ struct Workspace {
   void* arena = nullptr;
   __nv_bfloat16 *patches, *h, *qkv, *att, *mlp, *xin, *qk;
   float *x, *tokens, *pm, *ps, *pc, *wtab, *attn, *cvec, *rowscale, *heat, *pool, *pool_pe, *pooled, *feats, *focal_feat,
-      *fused, *depth, *conf, *mask_in, *tmpw, *tmpb, *exif_in, *cur_eps, *cur_noise, *cur_raw, *cur_reward;
+      *fused, *depth, *conf, *mask_in, *tmpw, *tmpb, *exif_in, *cur_eps, *cur_noise, *cur_raw, *cur_reward, *ln_stats;
   void* E;
   int* argmax;
   long long* cam_in;
@@ -277,6 +277,7 @@ int get_workspace(ca_handle* h, int B, int S, Workspace** out) {
   want(&w.patches, BN * ca::kPatchRowStride * 2);
   want(&w.x, M * kD * 4);
   want(&w.h, M * kD * 2);
+  want(&w.ln_stats, M * (kD / 128) * 2 * 4);
   want(&w.qkv, M * 3 * kD * 2);
   want(&w.att, M * kD * 2);
   want(&w.mlp, M * kMlp * 2);
@@ -349,21 +350,62 @@ int gemm(ca_handle* h, const void* A, const void* W, int M, int N, int K, int ep
   return 0;
 }
 
+int gemm_ln(ca_handle* h, const void* A, const void* W, int M, int N, int K, int epi, void* out, int ldo, const float* bias,
+            const float* ls, float* stats, __nv_bfloat16* shadow, cudaStream_t st) {
+  ca::GemmArgs a{};
+  a.A = static_cast<const __nv_bfloat16*>(A);
+  a.W = static_cast<const __nv_bfloat16*>(W);
+  a.M = M;
+  a.N = N;
+  a.K = K;
+  a.lda = K;
+  a.ldw = K;
+  a.batch = 1;
+  a.epilogue = epi;
+  a.out = out;
+  a.ldo = ldo;
+  a.bias = bias;
+  a.ls = ls;
+  a.ln_stats = stats;
+  a.ln_slots = kD / 128;
+  a.ln_eps = 1e-6f;
+  a.shadow = shadow;
+  a.ld_shadow = kD;
+  LAUNCH(ca::gemm_launch(a, st));
+  return 0;
+}
+
 int backbone_layers(ca_handle* h, Workspace& w, const Tables& tb, cudaStream_t st) {
   const int B = w.B, g = w.S / 14, N = g * g, T = N + 1, M = B * T;
   const ca_model_weights& mw = h->w;
   LAUNCH(ca::cls_rows_launch(w.x, mw.cls_token, tb.pos, B, T, kD, st));
   CA_TRY(gemm(h, w.patches, mw.patch_w, B * N, kD, ca::kPatchRowStride, ca::EPI_PATCH_F32, w.x, kD, mw.patch_b, nullptr, tb.pos, N, st,
               ca::kPatchRowStride, ca::kPatchRowStride));
+  // LayerNorm-folded operands (ca_model_weights.layernorm_folded): norm1 / norm2 live in the epilogues of the GEMMs either
+  // side of them; `w.h` then carries the raw residual rows as bf16 and `w.ln_stats` their statistics.
+  const bool fold = mw.layernorm_folded != 0;
+  if (fold) LAUNCH(ca::ln_shadow_launch(w.x, w.h, kD, w.ln_stats, M, kD, st));
   for (int l = 0; l < kLayers; ++l) {
     const ca_layer_weights& L = mw.layer[l];
-    LAUNCH(ca::layernorm_launch(w.x, L.n1w, L.n1b, w.h, 1, M, kD, 1e-6f, st));
-    CA_TRY(gemm(h, w.h, L.wqkv, M, 3 * kD, kD, ca::EPI_BIAS_BF16, w.qkv, 3 * kD, L.bqkv, nullptr, nullptr, 0, st));
+    if (fold) {
+      CA_TRY(gemm_ln(h, w.h, L.wqkv, M, 3 * kD, kD, ca::EPI_LN_BIAS_BF16, w.qkv, 3 * kD, L.bqkv, nullptr, w.ln_stats, nullptr, st));
+    } else {
+      LAUNCH(ca::layernorm_launch(w.x, L.n1w, L.n1b, w.h, 1, M, kD, 1e-6f, st));
+      CA_TRY(gemm(h, w.h, L.wqkv, M, 3 * kD, kD, ca::EPI_BIAS_BF16, w.qkv, 3 * kD, L.bqkv, nullptr, nullptr, 0, st));
+    }
     LAUNCH(ca::attention_launch(w.qkv, w.att, B, T, kHeads, st));
-    CA_TRY(gemm(h, w.att, L.wo, M, kD, kD, ca::EPI_RESID_F32, w.x, kD, L.bo, L.ls1, nullptr, 0, st));
-    LAUNCH(ca::layernorm_launch(w.x, L.n2w, L.n2b, w.h, 1, M, kD, 1e-6f, st));
-    CA_TRY(gemm(h, w.h, L.w1, M, kMlp, kD, ca::EPI_GELU_BF16, w.mlp, kMlp, L.b1, nullptr, nullptr, 0, st));
-    CA_TRY(gemm(h, w.mlp, L.w2, M, kD, kMlp, ca::EPI_RESID_F32, w.x, kD, L.b2, L.ls2, nullptr, 0, st));
+    if (fold) {
+      CA_TRY(gemm_ln(h, w.att, L.wo, M, kD, kD, ca::EPI_RESID_LN_F32, w.x, kD, L.bo, L.ls1, w.ln_stats, w.h, st));
+      CA_TRY(gemm_ln(h, w.h, L.w1, M, kMlp, kD, ca::EPI_LN_GELU_BF16, w.mlp, kMlp, L.b1, nullptr, w.ln_stats, nullptr, st));
+    } else {
+      CA_TRY(gemm(h, w.att, L.wo, M, kD, kD, ca::EPI_RESID_F32, w.x, kD, L.bo, L.ls1, nullptr, 0, st));
+      LAUNCH(ca::layernorm_launch(w.x, L.n2w, L.n2b, w.h, 1, M, kD, 1e-6f, st));
+      CA_TRY(gemm(h, w.h, L.w1, M, kMlp, kD, ca::EPI_GELU_BF16, w.mlp, kMlp, L.b1, nullptr, nullptr, 0, st));
+    }
+    if (fold && l + 1 < kLayers)
+      CA_TRY(gemm_ln(h, w.mlp, L.w2, M, kD, kMlp, ca::EPI_RESID_LN_F32, w.x, kD, L.b2, L.ls2, w.ln_stats, w.h, st));
+    else  // the final LayerNorm reads the fp32 rows itself
+      CA_TRY(gemm(h, w.mlp, L.w2, M, kD, kMlp, ca::EPI_RESID_F32, w.x, kD, L.b2, L.ls2, nullptr, 0, st));
   }
   LAUNCH(ca::layernorm_launch(w.x, mw.lnw, mw.lnb, w.tokens, 0, M, kD, 1e-6f, st));
   return 0;
@@ -582,6 +624,10 @@ int ca_create(ca_handle** out, const ca_model_weights* w, int device) {
   CA_TRY(ca_device_check(device));
   CA_REQUIRE(w->n_focal >= 1 && w->n_focal <= 4, "ca_create: 1..4 focal iterations are built");
   CA_REQUIRE(w->pos_embed && w->patch_w && w->cls_token && w->lnw, "ca_create: null weight");
+  for (int l = 0; l < kLayers; ++l) {
+    const ca_layer_weights& L = w->layer[l];
+    CA_REQUIRE(w->layernorm_folded || (L.n1w && L.n1b && L.n2w && L.n2b), "ca_create: null LayerNorm weight");
+  }
   DeviceGuard guard(device);
   ca_handle* h = new ca_handle();
   h->w = *w;

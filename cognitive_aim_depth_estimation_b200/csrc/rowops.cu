@@ -2,6 +2,8 @@
 // All are one-pass, 128-bit vectorised, coalesced along the contiguous dimension; their roofline is HBM.
 #include "common.cuh"
 #include "host.h"
+
+#include <stdlib.h>
 #include "rowops.cuh"
 
 namespace ca {
@@ -121,11 +123,14 @@ __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__
 template <int D, typename OutT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, OutT* __restrict__ out, int rows,
-                                                         float eps, int ld_out) {
+                                                         float eps, int ld_out, int reverse) {
   griddep_sync();  // PDL: nothing before this line reads or writes global memory
   constexpr int kVec = D / 128;  // float4 per lane
-  const int row = blockIdx.x * (blockDim.x >> 5) + warp_id();
+  int row = blockIdx.x * (blockDim.x >> 5) + warp_id();
   if (row >= rows) return;
+  // the GEMM before this kernel wrote the rows in ascending order, so the LAST rows are the ones still in the L2:
+  // start there (the block scheduler hands out blockIdx in ascending order)
+  if (reverse) row = rows - 1 - row;
   const int lane = lane_id();
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
   float4 v[kVec];
@@ -161,6 +166,40 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ld_out)[lane + 32 * i] = y;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Entry of the LayerNorm-folded layer chain (gemm.cuh, EPI_LN_* / EPI_RESID_LN_F32): what the residual epilogue leaves
+// behind for every later layer, produced here for the rows the embedding wrote — the raw rows as bf16 and, per 128-column
+// span (the 4 floats x 32 lanes of one register slot), the sum and the sum of squared deviations from the span mean.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) ln_shadow_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ shadow,
+                                                         int ld_shadow, float2* __restrict__ stats, int rows) {
+  griddep_sync();  // PDL: nothing before this line reads or writes global memory
+  constexpr int kVec = D / 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp_id();
+  if (row >= rows) return;
+  const int lane = lane_id();
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+  float4 v[kVec];
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) v[i] = xr[lane + 32 * i];
+  float mine_sum = 0.f, mine_m2 = 0.f;  // lane i keeps span i
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    const float sum = warp_sum((v[i].x + v[i].y) + (v[i].z + v[i].w));
+    const float m = sum * (1.0f / 128.f);
+    const float a = v[i].x - m, b = v[i].y - m, c = v[i].z - m, d = v[i].w - m;
+    const float m2 = warp_sum((a * a + b * b) + (c * c + d * d));
+    if (lane == i) {
+      mine_sum = sum;
+      mine_m2 = m2;
+    }
+    reinterpret_cast<uint2*>(shadow + static_cast<size_t>(row) * ld_shadow)[lane + 32 * i] =
+        make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+  }
+  if (lane < kVec) stats[static_cast<size_t>(row) * kVec + lane] = make_float2(mine_sum, mine_m2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -261,11 +300,24 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, void
   CA_REQUIRE(D == 768, "layernorm: only D = 768 (ViT-B) is instantiated");
   CA_REQUIRE(rows > 0, "layernorm: no rows");
   const int grid = (rows + 7) / 8;
+  static const int reverse = getenv("CA_LN_FORWARD") ? 0 : 1;
   if (out_is_bf16)
     CA_TRY(launch_kernel(layernorm_kernel<768, __nv_bfloat16>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, static_cast<__nv_bfloat16*>(out),
-                                                                   rows, eps, ld_out));
+                                                                   rows, eps, ld_out, reverse));
   else
-    CA_TRY(launch_kernel(layernorm_kernel<768, float>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, static_cast<float*>(out), rows, eps, ld_out));
+    CA_TRY(launch_kernel(layernorm_kernel<768, float>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, static_cast<float*>(out), rows, eps, ld_out, reverse));
+  CA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ln_shadow_launch(const float* x, __nv_bfloat16* shadow, int ld_shadow, float* stats, int rows, int D,
+                     cudaStream_t stream) {
+  CA_REQUIRE(x && shadow && stats, "ln_shadow: null pointer");
+  CA_REQUIRE(D == 768, "ln_shadow: only D = 768 (ViT-B) is instantiated");
+  CA_REQUIRE(rows > 0, "ln_shadow: no rows");
+  CA_REQUIRE(ld_shadow >= D && ld_shadow % 4 == 0, "ln_shadow: the shadow rows must be >= D wide and 8-byte aligned");
+  CA_TRY(launch_kernel(ln_shadow_kernel<768>, dim3((rows + 7) / 8), dim3(256), 0, stream, x, shadow, ld_shadow,
+                       reinterpret_cast<float2*>(stats), rows));
   CA_CUDA(cudaGetLastError());
   return 0;
 }

@@ -257,6 +257,16 @@ class CognitiveAimModel(nn.Module):
     def _lora_fused(self) -> bool:
         return self.cfg.use_lora and self.cfg.lora_mode == "fused"
 
+    def _ln_folded(self) -> bool:
+        """CA_LN_FOLD=1 (read when the operands are packed): norm1 / norm2 folded into the GEMMs either side of them
+        (ops.fold_layernorm, csrc/gemm.cuh EPI_LN_*) — no LayerNorm pass over HBM inside the encoder.  Opt-in: measured
+        at B = 32 x 518^2 it moves 0.88 ms / step out of `layernorm` and 0.78 ms into the residual GEMMs,
+        i.e. no faster than the separate kernels.  Never with fused LoRA adapters on q/k/v (their t = LN(x) A^T GEMM
+        wants the normalised rows)."""
+        if os.environ.get("CA_LN_FOLD", "0") in ("0", ""):
+            return False
+        return not (self._lora_fused() and self.cfg.lora_merge_target != "attention_output")
+
     def _write_lora(self, L, A, Bm):
         """Adapter (A [r, 768], B [768, r]) -> the packed operands of one layer: rows of `lora_a`, and the extra K columns
         of the target projection's weight, (alpha / r) * B in the rows of the adapted projection (zero elsewhere)."""
@@ -335,6 +345,11 @@ class CognitiveAimModel(nn.Module):
                 L["lora_a"] = torch.zeros(_LORA_PAD, _D, device=dev, dtype=torch.bfloat16)
                 del L[key]
                 self._write_lora(L, sd[f"lora_layers.{i}.lora_A"], sd[f"lora_layers.{i}.lora_B"])
+            if self._ln_folded():
+                wq = torch.cat([merged(sd[a + "query.weight"], "query"), merged(sd[a + "key.weight"], "key"),
+                                merged(sd[a + "value.weight"], "value")], 0).to(dev)
+                L["wqkv"], L["bqkv"] = ops.fold_layernorm(wq, L["bqkv"], L["n1w"], L["n1b"])
+                L["w1"], L["b1"] = ops.fold_layernorm(sd[p + "mlp.fc1.weight"].to(dev), L["b1"], L["n2w"], L["n2b"])
             layers.append(L)
         pk["layers"] = layers
         pk["zero64"] = torch.zeros(_LORA_PAD, device=dev)
@@ -461,6 +476,8 @@ class CognitiveAimModel(nn.Module):
                 "wtab": torch.empty(B, N, P, **fl),
                 "attn": torch.empty(self.cfg.num_iterations, B, N, **fl), "cvec": torch.empty(B, N, **fl),
                 "rowscale": torch.empty(2, B, N, **fl),
+                # LayerNorm folding: per (row, 128-column span) (sum, M2) of the residual row; `h` then holds the raw rows
+                "ln_stats": torch.empty(B * T, _D // 128, 2, **fl),
                 "heat": torch.empty(B, N, **fl), "argmax": torch.empty(B, device=dev, dtype=torch.int32),
                 "pool": torch.empty(B, _POOL_SPLITS, _D, **fl), "pool_pe": torch.empty(B, _POOL_SPLITS, _D, **fl),
                 "pooled": torch.empty(B, _D, **fl), "feats": torch.empty(B, self.cfg.num_iterations, 64, **fl),
@@ -590,23 +607,37 @@ class CognitiveAimModel(nn.Module):
             ops.gemm(patches, pk["patch_w"], ops.EPI_PATCH_F32, x, bias=pk["patch_b"], pos=tb["pos"], patches_per_img=N)
         fused = self._lora_fused()
         on_out = fused and self.cfg.lora_merge_target == "attention_output"
+        fold = self._ln_folded()
+        st = ws["ln_stats"]
+        if fold:
+            ops.ln_shadow(x, h, st)  # the residual epilogues keep (h, st) current from here on
         for li, L in enumerate(pk["layers"]):
           with _nvtx(f"cogaim.layer{li}"):
-            ops.layernorm(x, L["n1w"], L["n1b"], h)
-            if fused and not on_out:
-                ops.gemm(h, L["lora_a"], ops.EPI_BIAS_BF16, ws["h_ext"][:, _D:], bias=pk["zero64"])  # t = h A^T
-                ops.gemm(ws["h_ext"], L["wqkv_ext"], ops.EPI_BIAS_BF16, ws["qkv"], bias=L["bqkv"])
+            last = li == len(pk["layers"]) - 1
+            if fold:
+                ops.gemm_ln(h, L["wqkv"], ops.EPI_LN_BIAS_BF16, ws["qkv"], bias=L["bqkv"], stats=st)
             else:
-                ops.gemm(h, L["wqkv"], ops.EPI_BIAS_BF16, ws["qkv"], bias=L["bqkv"])
+                ops.layernorm(x, L["n1w"], L["n1b"], h)
+                if fused and not on_out:
+                    ops.gemm(h, L["lora_a"], ops.EPI_BIAS_BF16, ws["h_ext"][:, _D:], bias=pk["zero64"])  # t = h A^T
+                    ops.gemm(ws["h_ext"], L["wqkv_ext"], ops.EPI_BIAS_BF16, ws["qkv"], bias=L["bqkv"])
+                else:
+                    ops.gemm(h, L["wqkv"], ops.EPI_BIAS_BF16, ws["qkv"], bias=L["bqkv"])
             ops.attention(ws["qkv"], ws["att"], B, T, _HEADS)
+            a_out, w_out = (ws["att_ext"], L["wo_ext"]) if on_out else (ws["att"], L["wo"])
             if on_out:
                 ops.gemm(ws["att"], L["lora_a"], ops.EPI_BIAS_BF16, ws["att_ext"][:, _D:], bias=pk["zero64"])
-                ops.gemm(ws["att_ext"], L["wo_ext"], ops.EPI_RESID_F32, x, bias=L["bo"], ls=L["ls1"])
+            if fold:
+                ops.gemm_ln(a_out, w_out, ops.EPI_RESID_LN_F32, x, bias=L["bo"], ls=L["ls1"], stats=st, shadow=h)
+                ops.gemm_ln(h, L["w1"], ops.EPI_LN_GELU_BF16, ws["mlp"], bias=L["b1"], stats=st)
             else:
-                ops.gemm(ws["att"], L["wo"], ops.EPI_RESID_F32, x, bias=L["bo"], ls=L["ls1"])
-            ops.layernorm(x, L["n2w"], L["n2b"], h)
-            ops.gemm(h, L["w1"], ops.EPI_GELU_BF16, ws["mlp"], bias=L["b1"])
-            ops.gemm(ws["mlp"], L["w2"], ops.EPI_RESID_F32, x, bias=L["b2"], ls=L["ls2"])
+                ops.gemm(a_out, w_out, ops.EPI_RESID_F32, x, bias=L["bo"], ls=L["ls1"])
+                ops.layernorm(x, L["n2w"], L["n2b"], h)
+                ops.gemm(h, L["w1"], ops.EPI_GELU_BF16, ws["mlp"], bias=L["b1"])
+            if fold and not last:
+                ops.gemm_ln(ws["mlp"], L["w2"], ops.EPI_RESID_LN_F32, x, bias=L["b2"], ls=L["ls2"], stats=st, shadow=h)
+            else:  # the final LayerNorm reads the fp32 rows itself
+                ops.gemm(ws["mlp"], L["w2"], ops.EPI_RESID_F32, x, bias=L["b2"], ls=L["ls2"])
         with _nvtx("cogaim.final_norm"):
             ops.layernorm(x, pk["lnw"], pk["lnb"], ws["tokens"].view(B * T, _D))
         return ws["tokens"]

@@ -20,7 +20,15 @@ from . import _lib
 _D, _LAYERS = 768, 12
 
 
-def _pack(sd: Dict[str, torch.Tensor], dev: torch.device, num_cameras: int):
+def _fold(weight, bias, gamma, beta):
+    """LayerNorm (gamma, beta) folded into the Linear after it (include/cogaim_b200.h, ca_layer_weights.cqkv / c1):
+    W' = bf16(rows of W diag(gamma), centred), b' = b + W beta."""
+    w32 = weight.float()
+    wg = w32 * gamma.float()[None, :]
+    return (wg - wg.mean(dim=1, keepdim=True)).to(torch.bfloat16), bias.float() + w32 @ beta.float()
+
+
+def _pack(sd: Dict[str, torch.Tensor], dev: torch.device, num_cameras: int, fold_layernorm: bool = False):
     """reference state_dict -> (ca_model_weights, tensors to keep alive)."""
     keep = []
 
@@ -57,6 +65,16 @@ def _pack(sd: Dict[str, torch.Tensor], dev: torch.device, num_cameras: int):
         L.w1, L.b1 = b16(sd[p + "mlp.fc1.weight"]), f32(sd[p + "mlp.fc1.bias"])
         L.w2, L.b2 = b16(sd[p + "mlp.fc2.weight"]), f32(sd[p + "mlp.fc2.bias"])
         L.ls2 = f32(sd[p + "layer_scale2.lambda1"])
+        if fold_layernorm:
+            # norm1 -> (wqkv, bqkv), norm2 -> (w1, b1): the library then runs the encoder without LayerNorm passes
+            wq = torch.cat([sd[a + "query.weight"], sd[a + "key.weight"], sd[a + "value.weight"]], 0).detach().to(dev)
+            bq = torch.cat([sd[a + "query.bias"], sd[a + "key.bias"], sd[a + "value.bias"]], 0).detach().to(dev)
+            g1, be1 = sd[p + "norm1.weight"].detach().to(dev), sd[p + "norm1.bias"].detach().to(dev)
+            g2, be2 = sd[p + "norm2.weight"].detach().to(dev), sd[p + "norm2.bias"].detach().to(dev)
+            wp, bp = _fold(wq, bq, g1, be1)
+            L.wqkv, L.bqkv = b16(wp), f32(bp)
+            wp, bp = _fold(sd[p + "mlp.fc1.weight"].detach().to(dev), sd[p + "mlp.fc1.bias"].detach().to(dev), g2, be2)
+            L.w1, L.b1 = b16(wp), f32(bp)
     w.lnw, w.lnb = f32(sd["backbone.layernorm.weight"]), f32(sd["backbone.layernorm.bias"])
     n_focal = 0
     while f"focal_stream.focal_streams.{n_focal}.query_proj.weight" in sd:
@@ -105,6 +123,7 @@ def _pack(sd: Dict[str, torch.Tensor], dev: torch.device, num_cameras: int):
     ptr = sd[c + "history_pointer"].detach().to(dev, torch.int64).reshape(1).contiguous().clone()
     w.exploration_history, w.history_len, w.history_pointer = hist.data_ptr(), hist.numel(), ptr.data_ptr()
     w.num_cameras = num_cameras
+    w.layernorm_folded = 1 if fold_layernorm else 0
     return w, keep, hist, ptr
 
 
@@ -112,13 +131,14 @@ class NativeModel:
     """`forward_with_guidance` / `forward` / backbone tokens through the handle-level C-ABI."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda:0", num_cameras: int = 71,
-                 use_graph: bool = True):
+                 use_graph: bool = True, fold_layernorm: bool = False):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("the Cognitive-Aim B200 path runs only on a CUDA sm_100 device; there is no CPU fallback")
         self.lib = _lib.load()
         self.use_graph = use_graph
-        w, self._keep, self.exploration_history, self.history_pointer = _pack(state_dict, self.device, num_cameras)
+        w, self._keep, self.exploration_history, self.history_pointer = _pack(state_dict, self.device, num_cameras,
+                                                                              fold_layernorm)
         h = C.c_void_p()
         _lib.check(self.lib.ca_create(C.byref(h), C.byref(w), self.device.index or 0), "ca_create")
         self._h = h

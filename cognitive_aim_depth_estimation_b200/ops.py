@@ -19,6 +19,7 @@ EPI_PATCH_F32 = 3
 EPI_ROWSTATS = 4
 EPI_COLSUM = 5
 EPI_F32 = 6
+EPI_LN_BIAS_BF16, EPI_LN_GELU_BF16, EPI_RESID_LN_F32 = 7, 8, 9
 
 
 class _Trace:
@@ -107,6 +108,50 @@ def gemm(A, W, epilogue, out=None, *, M=None, N=None, K=None, lda=None, ldw=None
     check(st, "ca_gemm_bf16")
     _end(e0, "gemm_stats" if epilogue in (EPI_ROWSTATS, EPI_COLSUM) else "gemm", 1, 2.0 * M * N * K * batch)
     return out
+
+
+def gemm_ln(A, W, epilogue, out, *, bias, stats, ls=None, shadow=None, eps=1e-6):
+    """The LayerNorm-folded forms of `gemm` (csrc/gemm.cuh EPI_LN_* / EPI_RESID_LN_F32; include/cogaim_b200.h
+    ca_gemm_bf16_ln).  stats: fp32 [M, slots, 2]."""
+    lib = _lib.load()
+    _req(A, torch.bfloat16, "A")
+    _req(W, torch.bfloat16, "W")
+    for t, n in ((bias, "bias"), (ls, "ls"), (stats, "stats")):
+        _req(t, torch.float32, n)
+    _req(shadow, torch.bfloat16, "shadow")
+    M, K, N = A.shape[-2], A.shape[-1], W.shape[-2]
+    e0 = _begin()
+    st = lib.ca_gemm_bf16_ln(ptr(A), ptr(W), M, N, K, A.stride(-2), W.stride(-2), epilogue, ptr(out), out.stride(-2),
+                             ptr(bias), ptr(ls), ptr(stats), stats.shape[-2], float(eps), ptr(shadow),
+                             shadow.stride(-2) if shadow is not None else 0, stream_ptr())
+    check(st, "ca_gemm_bf16_ln")
+    _end(e0, "gemm", 1, 2.0 * M * N * K)
+    return out
+
+
+def fold_layernorm(weight, bias, gamma, beta):
+    """Operands of an EPI_LN_* GEMM from a Linear (weight [N, K], bias [N]) and the LayerNorm (gamma, beta [K]) in front of
+    it:  LN(x) W^T + b = rstd * (x W'^T) + b'  with  W' = bf16(rows of W diag(gamma), centred)  and  b' = b + W beta.
+    Centring the rows (sum_k W'[n,k] = 0) makes x W'^T = (x - mean(x)) W'^T: the GEMM on the RAW rows already carries the
+    mean subtraction, and the epilogue is left with the row's 1/std."""
+    w32 = weight.float()
+    wg = w32 * gamma.float()[None, :]
+    wp = (wg - wg.mean(dim=1, keepdim=True)).to(torch.bfloat16).contiguous()
+    bp = (bias.float() + w32 @ beta.float()).contiguous()
+    return wp, bp
+
+
+def ln_shadow(x, shadow, stats):
+    """bf16 copy of the fp32 rows + the per-128-column (sum, M2) row statistics: entry of the LayerNorm-folded chain."""
+    _req(x, torch.float32, "x")
+    _req(shadow, torch.bfloat16, "shadow")
+    _req(stats, torch.float32, "stats")
+    rows, D = x.shape[-2], x.shape[-1]
+    e0 = _begin()
+    check(_lib.load().ca_ln_shadow(ptr(x), ptr(shadow), shadow.stride(-2), ptr(stats), rows, D, stream_ptr()),
+          "ca_ln_shadow")
+    _end(e0, "layernorm", 1, 0.0)
+    return shadow
 
 
 LOG2E = math.log2(math.e)

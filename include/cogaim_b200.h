@@ -41,7 +41,11 @@ typedef enum ca_epilogue {
   CA_EPI_ROWSTATS = 4,  /* softmax row statistics of acc*scale        src/model.py:197-200 (pass A); with `out` != NULL also keeps
                            exp2(acc*scale - span max) as fp16 [batch, M, ldo] for ca_colsum_e */
   CA_EPI_COLSUM = 5,    /* column sums of softmax(acc*scale)          src/model.py:234 (pass B, transposed) */
-  CA_EPI_F32 = 6        /* out_f32 = acc (test hook) */
+  CA_EPI_F32 = 6,       /* out_f32 = acc (test hook) */
+  /* LayerNorm (HF modeling_dinov2.py:354,359: norm1 / norm2) folded into the GEMMs either side of it — see ca_gemm_bf16_ln */
+  CA_EPI_LN_BIAS_BF16 = 7, /* out_bf16 = rstd * acc + bias, W row-centred                (norm1 -> q/k/v Linear) */
+  CA_EPI_LN_GELU_BF16 = 8, /* out_bf16 = gelu_erf(the same)                              (norm2 -> fc1 -> GELU) */
+  CA_EPI_RESID_LN_F32 = 9  /* x_f32 += ls * (acc + bias); shadow_bf16 = bf16(x); row statistics of the new x */
 } ca_epilogue;
 
 /* Library / device introspection -------------------------------------------------------------- */
@@ -59,6 +63,19 @@ int ca_gemm_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K, int 
                  long long out_batch_stride, const float* bias, const float* ls, const float* pos,
                  int patches_per_img, float scale_log2, float* part_a, float* part_b, const float* col_max,
                  const float* col_rinv, void* stream);
+
+/* The same contraction with the LayerNorm of HF modeling_dinov2.py:354 / :359 folded in (no LayerNorm pass over HBM):
+ *   LN(x) W^T + b  =  rstd * (x W'^T) + b',   b' = b + W beta,   W' = W diag(gamma) with every row centred,
+ *   W'[n,:] -= mean_k W'[n,k]   (then x W'^T = (x - mean(x)) W'^T: the row mean never has to be subtracted).
+ * CA_EPI_RESID_LN_F32 (dense + LayerScale + residual, :246,278,376-385) updates x in place and leaves, for the LayerNorm
+ * that follows, `shadow` = the new rows as bf16 [M, N] (pitch ld_shadow) and ln_stats[M, ln_slots, 2] = (sum, sum of
+ * squared deviations from the span mean) of each 128-column span of the new row; N == 128 * ln_slots.
+ * CA_EPI_LN_BIAS_BF16 / CA_EPI_LN_GELU_BF16 take A = that shadow (K == 128 * ln_slots), W = W' (bf16), bias = b' and
+ * ln_stats, and apply the row's 1/sqrt(var + ln_eps) in the epilogue.  ca_ln_shadow produces shadow + ln_stats from fp32 rows (the entry of the chain, after the embeddings). */
+int ca_gemm_bf16_ln(const uint16_t* A, const uint16_t* W, int M, int N, int K, int lda, int ldw, int epilogue, void* out,
+                    int ldo, const float* bias, const float* ls, float* ln_stats, int ln_slots,
+                    float ln_eps, uint16_t* shadow, int ld_shadow, void* stream);
+int ca_ln_shadow(const float* x, uint16_t* shadow, int ld_shadow, float* stats, int rows, int D, void* stream);
 
 /* Backbone attention --------------------------------------------------------------------------- */
 /* out[B*T, H*64] = softmax(Q K^T / 8) V per (image, head); qkv is the fused [B*T, 3*H*64] activation
@@ -293,6 +310,9 @@ typedef struct ca_model_weights {
   int history_len;
   long long* history_pointer;   /* device int64 */
   int num_cameras;              /* rows of heads.cam_emb; 0 = the model has no EXIF prior */
+  int layernorm_folded;         /* 1 = the caller folded norm1 into (wqkv, bqkv) and norm2 into (w1, b1) of every layer
+                                   (W' = bf16(rows of W diag(gamma), centred), b' = b + W beta; see ca_gemm_bf16_ln): the
+                                   encoder runs without LayerNorm passes and n1w / n1b / n2w / n2b are not read */
 } ca_model_weights;
 
 /* Per-call inputs.  Device pointers unless marked HOST.  The two Gaussian draws of the CuriosityModule and the per-call

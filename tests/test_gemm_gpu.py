@@ -150,3 +150,87 @@ def test_focal_colsum_from_stored_exponentials(cuda_device, N, D):
         got = pc.sum(1)
         want = ref.sum(dim=1) if weight is None else (ref * weight[:, :, None]).sum(dim=1)
         assert torch.allclose(got, want, rtol=3e-3, atol=1e-6), ((got - want).abs() / want).max()
+
+
+def _stats_to_mean_var(stats):
+    """[M, slots, 2] (sum, M2) per 128-column span -> (mean, biased variance) per row (Chan's combination)."""
+    s, m2 = stats[..., 0].double(), stats[..., 1].double()
+    slots = stats.shape[1]
+    mean = s.sum(1) / (128 * slots)
+    var = (m2.sum(1) + (128 * (s / 128 - mean[:, None]) ** 2).sum(1)) / (128 * slots)
+    return mean, var
+
+
+@pytest.mark.parametrize("M", [8, 1370, 2741])
+def test_ln_shadow_rows_and_statistics(cuda_device, M):
+    from cognitive_aim_depth_estimation_b200 import ops
+    x = _rand((M, 768), cuda_device, 30, 3.0) + _rand((M, 1), cuda_device, 31, 2.0)
+    shadow = torch.zeros(M, 768, device=cuda_device, dtype=torch.bfloat16)
+    stats = torch.full((M, 6, 2), float("nan"), device=cuda_device)
+    ops.ln_shadow(x, shadow, stats)
+    torch.cuda.synchronize()
+    assert torch.equal(shadow, x.bfloat16())
+    mean, var = _stats_to_mean_var(stats)
+    assert torch.allclose(mean, x.double().mean(1), atol=1e-5)
+    assert torch.allclose(var, x.double().var(1, unbiased=False), rtol=1e-5)
+
+
+@pytest.mark.parametrize("M,K", [(40, 768), (1370, 768), (2741, 768), (1370 * 3, 3072), (300, 832)])
+def test_gemm_resid_ln_updates_rows_and_leaves_shadow_and_statistics(cuda_device, M, K):
+    """EPI_RESID_LN_F32: the residual update of EPI_RESID_F32 with the old rows read into the SM (TMA load, update in
+    shared memory, TMA store), plus what the LayerNorm after it needs: the new rows as bf16 and per-span (sum, M2)."""
+    from cognitive_aim_depth_estimation_b200 import ops
+    N = 768
+    A = _rand((M, K), cuda_device, 32).bfloat16()
+    W = _rand((N, K), cuda_device, 33, 0.03).bfloat16()
+    bias = _rand((N,), cuda_device, 34, 0.1)
+    ls = _rand((N,), cuda_device, 35, 1.0)
+    x0 = _rand((M, N), cuda_device, 36, 2.0) + 1.5
+    ref = x0 + ls * (A.float() @ W.float().t() + bias)
+    x = x0.clone()
+    shadow = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
+    stats = torch.full((M, 6, 2), float("nan"), device=cuda_device)
+    ops.gemm_ln(A, W, ops.EPI_RESID_LN_F32, x, bias=bias, ls=ls, stats=stats, shadow=shadow)
+    torch.cuda.synchronize()
+    assert torch.isfinite(x).all() and torch.isfinite(stats).all()
+    assert _relerr(x, ref) < 2e-5, _relerr(x, ref)
+    assert torch.equal(shadow, x.bfloat16())
+    mean, var = _stats_to_mean_var(stats)
+    assert torch.allclose(mean, x.double().mean(1), atol=2e-5)
+    assert torch.allclose(var, x.double().var(1, unbiased=False), rtol=2e-5)
+    # the plain reduce-add epilogue computes the same update
+    x2 = x0.clone()
+    ops.gemm(A, W, ops.EPI_RESID_F32, x2, bias=bias, ls=ls)
+    assert _relerr(x2, x) < 1e-6
+
+
+@pytest.mark.parametrize("M,N,gelu", [(1370, 2304, False), (2741, 3072, True), (40, 2304, False)])
+def test_gemm_with_folded_layernorm_matches_layernorm_then_gemm(cuda_device, M, N, gelu):
+    """EPI_LN_*: LayerNorm(x) W^T + b computed as rstd * (bf16(x) W'^T) + b' (row-centred W') from the raw rows and the
+    statistics buffer, against torch's LayerNorm + matmul in fp32, with a row mean comparable to the row deviation."""
+    from cognitive_aim_depth_estimation_b200 import ops
+    K = 768
+    x = _rand((M, K), cuda_device, 40, 2.0) + _rand((M, 1), cuda_device, 41, 1.0)
+    gamma = 1.0 + _rand((K,), cuda_device, 42, 0.2)
+    beta = _rand((K,), cuda_device, 43, 0.1)
+    W = _rand((N, K), cuda_device, 44, 0.03)
+    bias = _rand((N,), cuda_device, 45, 0.1)
+    ref = torch.nn.functional.layer_norm(x, (K,), gamma, beta, eps=1e-6) @ W.t() + bias
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    shadow = torch.zeros(M, K, device=cuda_device, dtype=torch.bfloat16)
+    stats = torch.zeros(M, 6, 2, device=cuda_device)
+    ops.ln_shadow(x, shadow, stats)
+    wp, bp = ops.fold_layernorm(W, bias, gamma, beta)
+    out = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
+    ops.gemm_ln(shadow, wp, ops.EPI_LN_GELU_BF16 if gelu else ops.EPI_LN_BIAS_BF16, out, bias=bp, stats=stats)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    # the unfused path (LayerNorm kernel -> bf16 -> GEMM) on the same inputs, for scale
+    h = torch.zeros(M, K, device=cuda_device, dtype=torch.bfloat16)
+    ops.layernorm(x, gamma, beta, h)
+    out2 = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
+    ops.gemm(h, W.bfloat16(), ops.EPI_GELU_BF16 if gelu else ops.EPI_BIAS_BF16, out2, bias=bias)
+    e_fold, e_plain = _relerr(out, ref), _relerr(out2, ref)
+    assert e_fold < 6e-3, (e_fold, e_plain)
+    assert e_fold < 2.0 * e_plain + 1e-3, (e_fold, e_plain)

@@ -61,7 +61,7 @@ def test_guided_forward_through_the_handle(native, sd, S):
                 torch.cuda.synchronize()
             _check(depth, conf, heat, ref)
             assert torch.equal(arg.cpu().long(), ref["heatmap"].argmax(-1))
-    assert native.launch_count() > 100
+    assert native.launch_count() > 80
     # an explicit guidance tensor of another grid size is the caller's to resize; one of the right size is taken as is
     g = S // 14
     guide = torch.rand(g * g, generator=torch.Generator().manual_seed(3)) * 3
@@ -111,6 +111,22 @@ def test_handle_matches_the_python_orchestration(native, sd, cuda_device):
     assert int(fresh.history_pointer) == int(m.curiosity_module.history_pointer) == 6
     assert torch.allclose(fresh.exploration_history[:6], m.curiosity_module.exploration_history[:6], rtol=1e-4, atol=1e-7)
     fresh.close()
+
+
+def test_handle_with_caller_folded_layernorm(sd, cuda_device):
+    """ca_model_weights.layernorm_folded = 1: the caller folds norm1 / norm2 into the q/k/v and fc1 operands and the handle
+    runs the encoder without LayerNorm passes (24 launches fewer); same tolerances against the oracle."""
+    from cognitive_aim_depth_estimation_b200.native import NativeModel
+    plain, folded = NativeModel(sd, device=cuda_device), NativeModel(sd, device=cuda_device, fold_layernorm=True)
+    x = orc.synthetic_images(2, 224)
+    ref = orc.dinov2_tokens(sd, x)
+    a, b = plain.backbone_tokens(x.cuda()).cpu(), folded.backbone_tokens(x.cuda()).cpu()
+    n_plain, n_folded = plain.launch_count(), folded.launch_count()
+    assert ((a - ref).norm() / ref.norm()).item() < 1.5e-2
+    assert ((b - ref).norm() / ref.norm()).item() < 1.5e-2
+    assert n_folded == n_plain - 24 + 1, (n_plain, n_folded)   # 24 LayerNorm launches gone, one ca_ln_shadow added
+    plain.close()
+    folded.close()
 
 
 def test_handle_errors_are_reported(native):

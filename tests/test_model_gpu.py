@@ -290,3 +290,48 @@ def test_uint8_images_through_the_forward(model, cases):
     assert torch.equal(a[2].argmax(-1), b[2].argmax(-1))
     with pytest.raises(ValueError):
         model.forward_with_guidance(u8, exg, "right")          # not square and no input_size
+
+
+def test_layernorm_folded_backbone_and_guided_forward_match_the_oracle(cuda_device, sd, cases, monkeypatch):
+    """CA_LN_FOLD=1: norm1 / norm2 folded into the GEMMs either side of them (no LayerNorm pass inside the encoder) — the
+    same oracle tolerances as the default path."""
+    from cognitive_aim_depth_estimation_b200.model import create_model
+    monkeypatch.setenv("CA_LN_FOLD", "1")
+    m = create_model(CFG, {"num_cameras": 71}, device=cuda_device)
+    m.load_state_dict(sd)
+    assert m._ln_folded()
+    for (S, B), (x, ex, ref_tok) in cases.items():
+        tok = m.backbone_tokens(x.cuda()).cpu()
+        rel = ((tok - ref_tok).norm() / ref_tok.norm()).item()
+        assert torch.isfinite(tok).all() and rel < TOKEN_REL_FRO, rel
+        torch.manual_seed(11)
+        ref = orc.forward_with_guidance(sd, None, ex, "left", tokens=ref_tok, update_history=False)
+        torch.manual_seed(11)
+        depth, conf, heat = m.forward_with_guidance(x.cuda(), _cuda_exif(ex, "cuda"), "left", return_attention=True)
+        assert ((depth.cpu() - ref["depth"]).abs() / ref["depth"].abs()).max().item() <= DEPTH_ABS_REL
+        assert (conf.cpu() - ref["confidence"]).abs().max().item() <= CONF_MAX_ABS
+        assert (heat.cpu() - ref["heatmap"]).abs().max().item() <= HEAT_MAX_ABS
+        assert torch.equal(heat.cpu().argmax(-1), ref["heatmap"].argmax(-1))
+
+
+def test_layernorm_folding_with_a_fused_lora_adapter_on_the_attention_output(cuda_device, monkeypatch):
+    """CA_LN_FOLD=1 with lora_mode: fused on attention_output: the residual epilogue that feeds norm2 runs with K = 832."""
+    from cognitive_aim_depth_estimation_b200.model import create_model
+    monkeypatch.setenv("CA_LN_FOLD", "1")
+    sd = _lora_sd(0.5)
+    merged = dict(sd)
+    for i in range(12):
+        k = f"backbone.encoder.layer.{i}.attention.output.dense.weight"
+        merged[k] = sd[k] + sd[f"lora_layers.{i}.lora_B"] @ sd[f"lora_layers.{i}.lora_A"]
+    x = orc.synthetic_images(2, 224)
+    want = orc.dinov2_tokens(merged, x)
+    m = create_model(dict(CFG, use_lora=True, lora_merge_target="attention_output", lora_mode="fused"),
+                     {"num_cameras": 71}, device=cuda_device)
+    m.load_state_dict(sd)
+    assert m._ln_folded()
+    tok = m.backbone_tokens(x.cuda()).cpu()
+    assert ((tok - want).norm() / want.norm()).item() < TOKEN_REL_FRO
+    # fused adapters on q/k/v need the normalised rows: folding steps aside
+    m2 = create_model(dict(CFG, use_lora=True, lora_merge_target="query", lora_mode="fused"), {"num_cameras": 71},
+                      device=cuda_device)
+    assert not m2._ln_folded()
