@@ -590,11 +590,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
 }
 
 constexpr int kMaxDevices = 64;
-constexpr unsigned kCounterRing = 1024;
+constexpr unsigned kCounterRing = 1024;     // slots recycled among eager launches
+constexpr unsigned kCapturedSlots = 65536;  // slots handed out ONCE to launches recorded into a CUDA graph
 struct DeviceState {
-  int* ring = nullptr;
+  int* ring = nullptr;  // kCounterRing + kCapturedSlots (work counter, exit counter) pairs, zero when idle
   int sms = 0;
   std::atomic<unsigned> next{0};
+  std::atomic<unsigned> next_captured{0};
 };
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mu;
@@ -617,8 +619,8 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
     if (!st.ring) {
       CA_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
       CA_CUDA(cudaDeviceGetAttribute(&st.sms, cudaDevAttrMultiProcessorCount, dev));
-      CA_CUDA(cudaMalloc(&st.ring, 2 * kCounterRing * sizeof(int)));
-      CA_CUDA(cudaMemset(st.ring, 0, 2 * kCounterRing * sizeof(int)));
+      CA_CUDA(cudaMalloc(&st.ring, 2 * (kCounterRing + kCapturedSlots) * sizeof(int)));
+      CA_CUDA(cudaMemset(st.ring, 0, 2 * (kCounterRing + kCapturedSlots) * sizeof(int)));
       CA_CUDA(cudaDeviceSynchronize());  // (first use only: the zeroes must be in place whatever stream launches first)
     }
   }
@@ -639,8 +641,20 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
   // different streams never share a counter.  A slot is zero when its launch starts (zeroed at allocation, re-zeroed by
   // the last CTA of the launch that used it 1024 launches earlier) — no memset node sits between the kernels of a
   // captured forward, so the programmatic dependency chain from the QKV GEMM to this kernel stays intact.  (A launch
-  // that faults leaves its slot dirty; a faulted context is unusable anyway.)
-  a.counter = st.ring + 2 * (st.next.fetch_add(1u) % kCounterRing);
+  // that faults leaves its slot dirty; a faulted context is unusable anyway.)  A launch that is being CAPTURED keeps its
+  // slot for as long as the graph may be replayed, so it gets one that is never handed out again: an eager launch or
+  // another graph running on a different stream can then never meet it on the same counter.
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  if (stream != nullptr && stream != cudaStreamLegacy)  // the legacy stream cannot capture, and asking it would
+    CA_CUDA(cudaStreamIsCapturing(stream, &capturing)); // invalidate a capture in progress on another stream
+  if (capturing == cudaStreamCaptureStatusActive) {
+    const unsigned slot = st.next_captured.fetch_add(1u);
+    CA_REQUIRE(slot < kCapturedSlots, "attention: more than 65536 attention launches have been captured into CUDA graphs in this "
+                                      "process (each keeps a work-counter slot for the life of the process)");
+    a.counter = st.ring + 2 * (kCounterRing + slot);
+  } else {
+    a.counter = st.ring + 2 * (st.next.fetch_add(1u) % kCounterRing);
+  }
   static const int stagger = getenv("CA_ATTN_STAGGER") ? atoi(getenv("CA_ATTN_STAGGER")) : 0;
   a.stagger = stagger;
   static const bool want_dbg = getenv("CA_ATTN_DEBUG") != nullptr;

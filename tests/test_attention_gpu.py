@@ -46,3 +46,39 @@ def test_attention_reference_jumps_mid_sequence(cuda_device):
     assert torch.isfinite(out.float()).all()
     rel = ((out.float() - ref).norm() / ref.norm()).item()
     assert rel < 8e-3, rel
+
+
+def test_captured_and_eager_launches_on_two_streams_do_not_share_a_work_counter(cuda_device):
+    """A launch recorded into a CUDA graph keeps its work-counter slot for the life of the graph; eager launches recycle a
+    separate ring.  Replay the graph on one stream while > 1024 eager launches (a full turn of that ring) run on
+    another: both results must stay exact."""
+    from cognitive_aim_depth_estimation_b200 import ops
+    B, T, H = 2, 333, 12
+    g = torch.Generator(device="cpu").manual_seed(5)
+    qkv1 = (torch.randn(B * T, 3 * H * 64, generator=g) * 0.5).to(cuda_device).bfloat16()
+    qkv2 = (torch.randn(B * T, 3 * H * 64, generator=g) * 0.5).to(cuda_device).bfloat16()
+    ref1, ref2 = torch.empty(B * T, H * 64, device=cuda_device, dtype=torch.bfloat16), torch.empty(B * T, H * 64, device=cuda_device, dtype=torch.bfloat16)
+    ops.attention(qkv1, ref1, B, T, H)
+    ops.attention(qkv2, ref2, B, T, H)
+    torch.cuda.synchronize()
+    out1, out2 = torch.zeros_like(ref1), torch.zeros_like(ref2)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s1):
+        with torch.cuda.graph(graph, stream=s1):
+            for _ in range(4):
+                ops.attention(qkv1, out1, B, T, H)
+    torch.cuda.synchronize()
+    for rep in range(6):
+        out1.zero_()
+        out2.zero_()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s1):
+            for _ in range(20):
+                graph.replay()
+        with torch.cuda.stream(s2):
+            for _ in range(200):
+                ops.attention(qkv2, out2, B, T, H)
+        torch.cuda.synchronize()
+        assert torch.equal(out1, ref1), rep
+        assert torch.equal(out2, ref2), rep

@@ -1,5 +1,5 @@
 """One LayerNorm-folded residual GEMM shape, a few launches: the target of an ncu capture.
-    python tools/run_one_gemm_ln.py proj|fc2|qkv|fc1"""
+    python tools/run_one_gemm_ln.py proj|fc2|qkv|fc1|fc1plain|qkvplain"""
 import os
 import sys
 
@@ -26,6 +26,12 @@ elif which == "fc2":
 elif which == "qkv":
     w, b, o = r(2304, 768, sc=.03).bfloat16(), r(2304), torch.empty(M, 2304, device=dev, dtype=torch.bfloat16)
     fn = lambda: ops.gemm_ln(h, w, ops.EPI_LN_BIAS_BF16, o, bias=b, stats=stats)  # noqa: E731
+elif which == "fc1plain":
+    w, b, o = r(3072, 768, sc=.03).bfloat16(), r(3072), torch.empty(M, 3072, device=dev, dtype=torch.bfloat16)
+    fn = lambda: ops.gemm(h, w, ops.EPI_GELU_BF16, o, bias=b)  # noqa: E731
+elif which == "qkvplain":
+    w, b, o = r(2304, 768, sc=.03).bfloat16(), r(2304), torch.empty(M, 2304, device=dev, dtype=torch.bfloat16)
+    fn = lambda: ops.gemm(h, w, ops.EPI_BIAS_BF16, o, bias=b)  # noqa: E731
 else:
     w, b, o = r(3072, 768, sc=.03).bfloat16(), r(3072), torch.empty(M, 3072, device=dev, dtype=torch.bfloat16)
     fn = lambda: ops.gemm_ln(h, w, ops.EPI_LN_GELU_BF16, o, bias=b, stats=stats)  # noqa: E731
