@@ -10,7 +10,7 @@ $CMD > gpurun_out/plain_${TAG}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 330 -c 240 --csv \
     --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launches_${TAG}.log 2>&1
 fi
-ncu --set full --clock-control none --import-source on -k regex:'gemm2?_tcgen05_kernel|attention_fwd_kernel' -s 150 -c 8 \
+[ -n "${LIST_ONLY:-}" ] || ncu --set full --clock-control none --import-source on -k regex:'gemm2?_tcgen05_kernel|attention_fwd_kernel' -s 150 -c 8 \
     -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
 tail -2 gpurun_out/plain_${TAG}.log | cut -c1-300
 tail -3 gpurun_out/ncu_full_${TAG}.log
