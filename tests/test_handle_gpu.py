@@ -97,7 +97,7 @@ def test_handle_matches_the_python_orchestration(native, sd, cuda_device):
     from cognitive_aim_depth_estimation_b200.native import NativeModel
     m = create_model({"model": {}}, {"num_cameras": 71}, device=cuda_device)
     m.load_state_dict(sd)
-    fresh = NativeModel(sd, device=cuda_device)
+    fresh = NativeModel(sd, device=cuda_device, fold_layernorm=m._ln_folded())  # same kernels, same operands
     x, ex = orc.synthetic_images(3, 518, seed=5), orc.synthetic_exif(3, seed=6)
     for instruction in ("left", "bottom"):
         torch.manual_seed(21)
