@@ -55,8 +55,10 @@ __global__ void __launch_bounds__(192) colsum_e_kernel(const __half* __restrict_
                                                         const float* __restrict__ wtab, float* __restrict__ pc, int N,
                                                         int P) {
   griddep_sync();  // PDL: nothing before this line reads or writes global memory
-  const int b = blockIdx.z;
-  const int p = blockIdx.y;
+  // The statistics GEMM wrote E image by image, row span by row span: walk it LAST-WRITTEN-FIRST, so that the CTAs that start
+  // first read what the L2 still holds (E of a batch is about the size of the L2) instead of evicting it unread.
+  const int b = gridDim.z - 1 - blockIdx.z;
+  const int p = gridDim.y - 1 - blockIdx.y;
   const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (j0 >= lde) return;
   const int span = j0 >> 6;
@@ -65,30 +67,39 @@ __global__ void __launch_bounds__(192) colsum_e_kernel(const __half* __restrict_
   const __half* e = E + static_cast<size_t>(b) * e_batch_stride + static_cast<size_t>(i0) * lde + j0;
   const float* w = wtab + (static_cast<size_t>(b) * N + i0) * P + span;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  // 16 rows per batch, ALL loads of a batch issued before the first use: 16 x 512 B in flight per warp.  (Written as one
-  // load-use loop the compiler kept two loads in flight per thread and the kernel sat at 0.38 of the HBM rate.)
-  constexpr int kBatch = 16;
-  for (int i = i0; i < i1; i += kBatch) {
-    uint4 q[kBatch];
-    float wi[kBatch];
+  // 8 rows per batch, double-buffered: the loads of batch k + 1 are issued before batch k is consumed, so a warp always has
+  // 8-16 x 512 B in flight.  (Written as one load-use loop the compiler kept two loads in flight per thread: 0.38 of the
+  // HBM rate; with 16-row batches consumed before the next batch was issued the memory pipe drained four times per CTA.)
+  constexpr int kBatch = 8;
+  uint4 q[2][kBatch];
+  float wi[2][kBatch];
+  auto fetch = [&](int buf, int i) {
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
       const bool in = i + u < i1;
-      q[u] = in ? __ldg(reinterpret_cast<const uint4*>(e + static_cast<size_t>(u) * lde)) : make_uint4(0u, 0u, 0u, 0u);
-      wi[u] = in ? __ldg(w + u * P) : 0.f;
+      q[buf][u] = in ? __ldg(reinterpret_cast<const uint4*>(e + static_cast<size_t>(i - i0 + u) * lde)) : make_uint4(0u, 0u, 0u, 0u);
+      wi[buf][u] = in ? __ldg(w + (i - i0 + u) * P) : 0.f;
     }
+  };
+  auto consume = [&](int buf) {
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
-      const __half2* h = reinterpret_cast<const __half2*>(&q[u]);
+      const __half2* h = reinterpret_cast<const __half2*>(&q[buf][u]);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float2 f = __half22float2(h[t]);
-        acc[2 * t + 0] = fmaf(f.x, wi[u], acc[2 * t + 0]);
-        acc[2 * t + 1] = fmaf(f.y, wi[u], acc[2 * t + 1]);
+        acc[2 * t + 0] = fmaf(f.x, wi[buf][u], acc[2 * t + 0]);
+        acc[2 * t + 1] = fmaf(f.y, wi[buf][u], acc[2 * t + 1]);
       }
     }
-    e += static_cast<size_t>(kBatch) * lde;
-    w += kBatch * P;
+  };
+  fetch(0, i0);
+#pragma unroll 1
+  for (int i = i0; i < i1; i += 2 * kBatch) {
+    fetch(1, i + kBatch);
+    consume(0);
+    fetch(0, i + 2 * kBatch);
+    consume(1);
   }
   float* out = pc + (static_cast<size_t>(b) * P + p) * N + j0;
 #pragma unroll
@@ -101,7 +112,9 @@ __global__ void __launch_bounds__(192) colsum_e_kernel(const __half* __restrict_
 // mode 0: FocalStream attention  (mean over rows, centre bias, L1, clamp, renorm)   src/model.py:234-282
 // mode 1: plain sum of partials (weighted column sums for the un-guided value path; no bias / normalisation)
 // cur_weight[b] (optional): curiosity modulation between the L1 normalisation and the clamp (src/model.py:264-276).
-__global__ void __launch_bounds__(256) focal_finalize_kernel(const float* __restrict__ pc, const float* __restrict__ cbias,
+constexpr int kFinalizeThreads = 1024;
+constexpr int kFinalizeCols = 8;  // columns a thread keeps in registers: N <= 8192 (1036 x 1036 images: N = 5476)
+__global__ void __launch_bounds__(kFinalizeThreads) focal_finalize_kernel(const float* __restrict__ pc, const float* __restrict__ cbias,
                                                               float* __restrict__ attn, const float* __restrict__ rs_in,
                                                               float* __restrict__ rs_out, int N, int P,
                                                               float focus_strength, int mode,
@@ -113,34 +126,58 @@ __global__ void __launch_bounds__(256) focal_finalize_kernel(const float* __rest
   const float* pcb = pc + static_cast<size_t>(b) * P * N;
   float* ab = attn + static_cast<size_t>(b) * N;
   const float invN = 1.0f / static_cast<float>(N);
+  // A latency kernel (one CTA per image, 130 KB of partials): every thread owns up to 8 columns and keeps them in
+  // registers through the three passes; the P partials of a column are fetched 8 at a time (independent loads) and
+  // added in ascending order — the same sums as a plain loop, without one L2 round trip per addend.
+  float v[kFinalizeCols];
   float local = 0.f;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    float s = 0.f;
-    for (int i = 0; i < P; ++i) s += pcb[static_cast<size_t>(i) * N + j];
-    const float v = (mode == 0) ? (s * invN + cbias[j]) : s;
-    ab[j] = v;
-    local += v;
+#pragma unroll
+  for (int c = 0; c < kFinalizeCols; ++c) {
+    const int j = threadIdx.x + c * kFinalizeThreads;
+    v[c] = 0.f;
+    if (j < N) {
+      float s = 0.f;
+      for (int i = 0; i < P; i += 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = (i + u < P) ? pcb[static_cast<size_t>(i + u) * N + j] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (i + u < P) s += t[u];
+      }
+      v[c] = (mode == 0) ? (s * invN + cbias[j]) : s;
+      local += v[c];
+      if (mode != 0) ab[j] = v[c];
+    }
   }
   if (mode != 0) return;
   const float tot1 = block_sum(local, red);
   const float d1 = tot1 + 1e-8f;
   const float cw = cur_weight ? cur_weight[b] : 0.f;
   local = 0.f;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    float v = ab[j] / d1;
-    if (cur_weight) v = adaptive_weight * (v * (1.0f + cw)) + (1.0f - adaptive_weight) * v;  // src/model.py:270-274
-    v = fmaxf(v, 1e-8f);
-    ab[j] = v;
-    local += v;
+#pragma unroll
+  for (int c = 0; c < kFinalizeCols; ++c) {
+    const int j = threadIdx.x + c * kFinalizeThreads;
+    if (j < N) {
+      float a = v[c] / d1;
+      if (cur_weight) a = adaptive_weight * (a * (1.0f + cw)) + (1.0f - adaptive_weight) * a;  // src/model.py:270-274
+      a = fmaxf(a, 1e-8f);
+      v[c] = a;
+      local += a;
+    }
   }
   const float tot2 = block_sum(local, red);
   const float d2 = tot2 + 1e-8f;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    const float a = ab[j] / d2;
-    ab[j] = a;
-    if (rs_out) {
-      const size_t o = static_cast<size_t>(b) * N + j;
-      rs_out[o] = (rs_in ? rs_in[o] : 1.0f) * (1.0f + focus_strength * a);
+#pragma unroll
+  for (int c = 0; c < kFinalizeCols; ++c) {
+    const int j = threadIdx.x + c * kFinalizeThreads;
+    if (j < N) {
+      const float a = v[c] / d2;
+      ab[j] = a;
+      if (rs_out) {
+        const size_t o = static_cast<size_t>(b) * N + j;
+        rs_out[o] = (rs_in ? rs_in[o] : 1.0f) * (1.0f + focus_strength * a);
+      }
     }
   }
 }
@@ -269,7 +306,8 @@ int focal_finalize_launch(const float* pc, const float* cbias, float* attn, cons
                           cudaStream_t stream) {
   CA_REQUIRE(pc && attn, "focal_finalize: null pointer");
   CA_REQUIRE(mode != 0 || cbias, "focal_finalize: null centre bias");
-  CA_TRY(launch_kernel(focal_finalize_kernel, dim3(B), dim3(256), 0, stream, pc, cbias, attn, rs_in, rs_out, N, P, focus_strength, mode,
+  CA_REQUIRE(N <= kFinalizeThreads * kFinalizeCols, "focal_finalize: more than 8192 patch tokens per image");
+  CA_TRY(launch_kernel(focal_finalize_kernel, dim3(B), dim3(kFinalizeThreads), 0, stream, pc, cbias, attn, rs_in, rs_out, N, P, focus_strength, mode,
                                                   cur_weight, adaptive_weight));
   CA_CUDA(cudaGetLastError());
   return 0;
