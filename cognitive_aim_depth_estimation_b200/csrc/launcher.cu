@@ -597,7 +597,7 @@ int run_sequence(ca_handle* h, Workspace& w, int key, bool use_graph, cudaStream
 int check_call(const ca_handle* h, const ca_forward_call* c) {
   CA_REQUIRE(h && c, "null handle / call");
   CA_REQUIRE(c->images && c->B > 0, "forward: null images or empty batch");
-  CA_REQUIRE(c->S >= 56 && c->S % 14 == 0, "forward: image side must be a multiple of 14 and >= 56");
+  CA_REQUIRE(c->S >= 56 && c->S % 14 == 0 && c->S <= 1260, "forward: image side must be a multiple of 14 in [56, 1260]");
   CA_REQUIRE(c->depth && c->conf, "forward: null output");
   CA_REQUIRE(c->eps && c->noise, "forward: null CuriosityModule draws (HOST pointers, src/model.py:609,744)");
   return 0;

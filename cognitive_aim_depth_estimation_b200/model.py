@@ -39,6 +39,7 @@ _MLP = 3072
 _POOL_SPLITS = 32  # 1024 CTAs at B = 32: the 8-way split (256 CTAs) reached 39 % of the HBM rate (profiles/r01e_bw_kernels.md)
 _MAX_CURIOSITY_RUNS = 3
 _LORA_PAD = 64  # fused LoRA: the rank is padded to one 64-wide K block of the tcgen05 GEMM (K = 768 + 64 = 13 blocks)
+_MAX_SIDE = 1260  # 90 x 90 patch tokens: the focal vector stages keep an image's N <= 8192 columns in one CTA (csrc/focal.cu)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -552,14 +553,14 @@ class CognitiveAimModel(nn.Module):
             S = self.input_size if self.input_size is not None else H
             if self.input_size is None and H != W:
                 raise ValueError("uint8 images must be square, or set model.input_size to resize like demo.py")
-            if S < 56 or S % 14 != 0:
-                raise ValueError(f"image side must be a multiple of 14 and >= 56 (got {S})")
+            if S < 56 or S % 14 != 0 or S > _MAX_SIDE:
+                raise ValueError(f"image side must be a multiple of 14 in [56, {_MAX_SIDE}] (got {S})")
             return B, S
         if not torch.is_tensor(images) or images.dim() != 4 or images.shape[1] != 3:
             raise ValueError("images must be a [B, 3, S, S] tensor")
         B, _, H, W = images.shape
-        if H != W or H < 56:
-            raise ValueError(f"images must be square with side >= 56 (got {H} x {W})")
+        if H != W or H < 56 or H > _MAX_SIDE:
+            raise ValueError(f"images must be square with side in [56, {_MAX_SIDE}] (got {H} x {W})")
         if not images.is_floating_point():
             raise ValueError("images must be floating point (already normalised) or uint8 [B, H, W, 3]")
         return B, H
