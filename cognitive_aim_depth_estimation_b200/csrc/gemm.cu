@@ -136,41 +136,64 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
     // kSpan / 64 of them (one with 128-wide tiles, two with the 256-wide tiles of the CTA-pair kernel).
     // pass 1: max ; pass 2: sum exp2(s - max).  TMEM re-read is cheaper than holding the span in registers.
     constexpr int kSub = kSpan / 64;
+    const uint32_t stage_s = smem_u32(stage);
 #pragma unroll 1
     for (int sub = 0; sub < kSub; ++sub) {
       const int col_sub = col_base + sub * 64;
       const uint32_t taddr_sub = taddr + static_cast<uint32_t>(sub * 64);
+      // spans that lie wholly inside [0, N) — all but the last one or two of a row — skip the per-element bounds test
+      // (a compare and a select per score in an epilogue that already carries one MUFU per score)
+      const bool full = col_sub + 64 <= p.N;
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr_sub + c, v);
         tmem_ld_wait();
+        if (full) {
+          float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = __uint_as_float(v[j]) * p.scale_log2;
-          if (col_sub + c + j < p.N) mx = fmaxf(mx, s);
+          for (int j = 2; j < 32; j += 2) {
+            m0 = fmaxf(m0, __uint_as_float(v[j]));
+            m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+          }
+          mx = fmaxf(mx, fmaxf(m0, m1));  // raw scores: the (positive) scale is applied once, below
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col_sub + c + j < p.N) mx = fmaxf(mx, __uint_as_float(v[j]));
         }
       }
+      mx *= p.scale_log2;  // max_j (s_j * scale) = scale * max_j s_j  (scale > 0); fl(s * scale) is monotone in s
       float sum = 0.f;
       // optional: keep the span-relative exponentials E = exp2(s - span max) as fp16 so that the column sums of the
       // softmax are a bandwidth pass over E instead of a second Q K^T (ca_colsum_e)
-      __half* erow = p.out == nullptr ? nullptr
-                                      : reinterpret_cast<__half*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride +
-                                            static_cast<size_t>(row) * p.ldo + col_sub;
+      const bool keep_e = p.out != nullptr && col_sub < p.ldo;  // warp-uniform; ldo is a multiple of 64: whole spans
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr_sub + c, v);
         tmem_ld_wait();
         float ev[32];
+        if (full) {
+          float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = __uint_as_float(v[j]) * p.scale_log2;
-          ev[j] = (col_sub + c + j < p.N) ? fast_exp2(s - mx) : 0.f;
-          sum += ev[j];
+          for (int j = 0; j < 32; j += 2) {
+            ev[j] = fast_exp2(__uint_as_float(v[j]) * p.scale_log2 - mx);
+            ev[j + 1] = fast_exp2(__uint_as_float(v[j + 1]) * p.scale_log2 - mx);
+            s0 += ev[j];
+            s1 += ev[j + 1];
+          }
+          sum += s0 + s1;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float s = __uint_as_float(v[j]) * p.scale_log2;
+            ev[j] = (col_sub + c + j < p.N) ? fast_exp2(s - mx) : 0.f;
+            sum += ev[j];
+          }
         }
-        if (erow != nullptr && row_ok && col_sub + c < p.ldo) {  // ldo is a multiple of 64: whole 32-column pieces
+        if (keep_e) {  // thread-per-row -> the warp's swizzled staging buffer (16-byte piece 4 * (c / 32) + j / 8 of the row)
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint4 w;
@@ -180,9 +203,23 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
             w.y = *reinterpret_cast<uint32_t*>(&h1);
             w.z = *reinterpret_cast<uint32_t*>(&h2);
             w.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(erow + c + j) = w;
+            sts128(stage_s + epi_off(lane, (c >> 3) + (j >> 3)), w);
           }
         }
+      }
+      if (keep_e) {
+        // ... and out of it with 8 lanes per 128-byte row segment, 4 rows per instruction: whole lines per store (16-byte
+        // stores straight from the thread-per-row layout touch 32 different lines per instruction)
+        __syncwarp();
+        __half* ebase = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(b) * p.out_batch_stride + col_sub + (lane & 7) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = (lane >> 3) + 4 * i;
+          const int grow = mt * BM + quad * 32 + rr;
+          const uint4 w = lds128(stage_s + epi_off(rr, lane & 7));
+          if (grow < p.M) *reinterpret_cast<uint4*>(ebase + static_cast<size_t>(grow) * p.ldo) = w;
+        }
+        __syncwarp();
       }
       if (row_ok) {
         const size_t o = (static_cast<size_t>(b) * p.M + row) * p.partials + nt * (BN / 64) + half * kSub + sub;
