@@ -111,7 +111,7 @@ _SIGNATURES = {
     "ca_layernorm_ld": [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr],
     "ca_focal_input": [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr],
     "ca_fetch_pinned_f32": [c_ptr, c_ptr, C.c_size_t, c_ptr],
-    "ca_rowstats_merge": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr],
+    "ca_rowstats_merge": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr],
     "ca_colsum_e": [c_ptr, C.c_int, C.c_longlong, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr],
     "ca_focal_finalize": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, c_ptr,
                           C.c_float, c_ptr],

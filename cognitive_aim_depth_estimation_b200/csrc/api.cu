@@ -158,8 +158,9 @@ int ca_fetch_pinned_f32(float* dst, const float* h_src_pinned, size_t n, void* s
 }
 
 int ca_rowstats_merge(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, float* wtab,
-                      int rows, int P, void* stream) {
-  return ca::rowstats_merge_launch(pm, ps, weight, rmax, rinv, wtab, rows, P, static_cast<cudaStream_t>(stream));
+                      int rows, int rows_per_image, int P, void* stream) {
+  return ca::rowstats_merge_launch(pm, ps, weight, rmax, rinv, wtab, rows, rows_per_image, P,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 int ca_colsum_e(const uint16_t* E, int lde, long long e_batch_stride, const float* wtab, float* pc, int B, int N, int P,

@@ -24,26 +24,48 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;  // every thread holds the total
 }
 
-// pm, ps: [rows, P] (row max / sum-exp2 per 64-column span) -> rmax[rows], rinv[rows] = weight[row] / sum
-// wtab (optional): [rows, P], wtab[r, s] = exp2(m[r, s] - rmax[r]) * rinv[r] — the factor that turns the span-relative
-// exponentials E kept by GEMM pass A into (weighted) softmax probabilities.
-__global__ void rowstats_merge_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
+// pm, ps: [batch, P, N] span-major (row max / sum-exp2 per 64-column span, as CA_EPI_ROWSTATS writes them)
+//   -> rmax[batch * N], rinv[batch * N] = weight[row] / sum
+// wtab (optional): [batch, P, N], wtab[b, s, r] = exp2(m[b, s, r] - rmax[r]) * rinv[r] — the factor that turns the
+// span-relative exponentials E kept by GEMM pass A into (weighted) softmax probabilities.
+// One thread per row; with the span-major layout every load and store of a warp is one contiguous 128-byte line.
+constexpr int kMergeMaxSpans = 128;  // N <= 8192 columns
+__global__ void __launch_bounds__(256) rowstats_merge_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
                                       const float* __restrict__ weight, float* __restrict__ rmax,
-                                      float* __restrict__ rinv, float* __restrict__ wtab, int rows, int P) {
+                                      float* __restrict__ rinv, float* __restrict__ wtab, int rows, int N, int P) {
   griddep_sync();  // PDL: nothing before this line reads or writes global memory
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
-  const float* m = pm + static_cast<size_t>(r) * P;
-  const float* s = ps + static_cast<size_t>(r) * P;
+  const int b = r / N;
+  const size_t base = static_cast<size_t>(b) * P * N + (r - b * N);
+  const float* m = pm + base;
+  const float* s = ps + base;
   float mx = -INFINITY;
-  for (int i = 0; i < P; ++i) mx = fmaxf(mx, m[i]);
+  for (int i = 0; i < P; i += 8) {
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = (i + u < P) ? m[static_cast<size_t>(i + u) * N] : -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) mx = fmaxf(mx, t[u]);
+  }
   float sum = 0.f;
-  for (int i = 0; i < P; ++i) sum += s[i] * exp2f(m[i] - mx);  // s = 0 where the span is fully masked (m = -inf)
+  for (int i = 0; i < P; i += 8) {
+    float t[8], q[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool in = i + u < P;
+      t[u] = in ? m[static_cast<size_t>(i + u) * N] : -INFINITY;
+      q[u] = in ? s[static_cast<size_t>(i + u) * N] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (i + u < P) sum += q[u] * exp2f(t[u] - mx);  // s = 0 where the span is fully masked (m = -inf)
+  }
   const float ri = (weight ? weight[r] : 1.0f) / sum;
   if (rmax) rmax[r] = mx;
   if (rinv) rinv[r] = ri;
   if (wtab)
-    for (int i = 0; i < P; ++i) wtab[static_cast<size_t>(r) * P + i] = exp2f(m[i] - mx) * ri;
+    for (int i = 0; i < P; ++i) wtab[base + static_cast<size_t>(i) * N] = exp2f(m[static_cast<size_t>(i) * N] - mx) * ri;
 }
 
 // Column sums of the (weighted) row softmax from the stored exponentials: pc[b, p, j] = sum over the 64 rows i of row
@@ -65,7 +87,7 @@ __global__ void __launch_bounds__(192) colsum_e_kernel(const __half* __restrict_
   const int i0 = min(p * 64, N);
   const int i1 = min(i0 + 64, N);
   const __half* e = E + static_cast<size_t>(b) * e_batch_stride + static_cast<size_t>(i0) * lde + j0;
-  const float* w = wtab + (static_cast<size_t>(b) * N + i0) * P + span;
+  const float* w = wtab + (static_cast<size_t>(b) * P + span) * N + i0;  // span-major [B, P, N]: the rows of a span are contiguous
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   // 8 rows per batch, double-buffered: the loads of batch k + 1 are issued before batch k is consumed, so a warp always has
   // 8-16 x 512 B in flight.  (Written as one load-use loop the compiler kept two loads in flight per thread: 0.38 of the
@@ -78,7 +100,7 @@ __global__ void __launch_bounds__(192) colsum_e_kernel(const __half* __restrict_
     for (int u = 0; u < kBatch; ++u) {
       const bool in = i + u < i1;
       q[buf][u] = in ? __ldg(reinterpret_cast<const uint4*>(e + static_cast<size_t>(i - i0 + u) * lde)) : make_uint4(0u, 0u, 0u, 0u);
-      wi[buf][u] = in ? __ldg(w + (i - i0 + u) * P) : 0.f;
+      wi[buf][u] = in ? __ldg(w + (i - i0 + u)) : 0.f;
     }
   };
   auto consume = [&](int buf) {
@@ -281,10 +303,13 @@ __global__ void __launch_bounds__(192) weighted_pool_kernel(const float* __restr
 }  // namespace
 
 int rowstats_merge_launch(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, float* wtab,
-                          int rows, int P, cudaStream_t stream) {
+                          int rows, int rows_per_image, int P, cudaStream_t stream) {
   CA_REQUIRE(pm && ps, "rowstats_merge: null pointer");
   CA_REQUIRE((rmax && rinv) || wtab, "rowstats_merge: no output requested");
-  CA_TRY(launch_kernel(rowstats_merge_kernel, dim3((rows + 255) / 256), dim3(256), 0, stream, pm, ps, weight, rmax, rinv, wtab, rows, P));
+  CA_REQUIRE(P > 0 && P <= kMergeMaxSpans, "rowstats_merge: 1..128 spans per row");
+  CA_REQUIRE(rows > 0 && rows_per_image > 0 && rows % rows_per_image == 0, "rowstats_merge: rows must be batch * rows_per_image");
+  CA_TRY(launch_kernel(rowstats_merge_kernel, dim3((rows + 255) / 256), dim3(256), 0, stream, pm, ps, weight, rmax, rinv, wtab, rows,
+                       rows_per_image, P));
   CA_CUDA(cudaGetLastError());
   return 0;
 }

@@ -6,7 +6,7 @@
 namespace ca {
 
 int rowstats_merge_launch(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, float* wtab,
-                          int rows, int P, cudaStream_t stream);
+                          int rows, int rows_per_image, int P, cudaStream_t stream);
 int colsum_e_launch(const void* E, int lde, long long e_batch_stride, const float* wtab, float* pc, int B, int N, int P,
                     cudaStream_t stream);
 int focal_finalize_launch(const float* pc, const float* cbias, float* attn, const float* rs_in, float* rs_out, int B,

@@ -222,7 +222,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
         __syncwarp();
       }
       if (row_ok) {
-        const size_t o = (static_cast<size_t>(b) * p.M + row) * p.partials + nt * (BN / 64) + half * kSub + sub;
+        // span-major [batch, P, M]: the 32 rows of this warp are 128 contiguous bytes (row-major [batch, M, P] made every
+        // lane's 4-byte store its own sector, 2.1 M store requests per focal iteration)
+        const size_t o = (static_cast<size_t>(b) * p.partials + nt * (BN / 64) + half * kSub + sub) * p.M + row;
         p.part_a[o] = mx;
         p.part_b[o] = sum;
       }
@@ -247,7 +249,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelArgs& p, const CUt
       }
     }
     if (row_ok) {
-      const size_t o = (static_cast<size_t>(b) * p.M + row) * p.partials + nt * 2 + half;
+      const size_t o = (static_cast<size_t>(b) * p.partials + nt * 2 + half) * p.M + row;
       p.part_a[o] = sum;
     }
     return;

@@ -441,7 +441,7 @@ int focal_iterations(ca_handle* h, Workspace& w, const Tables& tb, bool want_fea
     a.part_a = w.pm;
     a.part_b = w.ps;
     LAUNCH(ca::gemm_launch(a, st));
-    LAUNCH(ca::rowstats_merge_launch(w.pm, w.ps, nullptr, nullptr, nullptr, w.wtab, B * N, w.P, st));
+    LAUNCH(ca::rowstats_merge_launch(w.pm, w.ps, nullptr, nullptr, nullptr, w.wtab, B * N, N, w.P, st));
     LAUNCH(ca::colsum_e_launch(w.E, w.lde, static_cast<long long>(N) * w.lde, w.wtab, w.pc, B, N, w.P, st));
     const bool last = i == mw.n_focal - 1;
     float* rs_out = last ? nullptr : w.rowscale + (i % 2) * BN;
@@ -449,7 +449,7 @@ int focal_iterations(ca_handle* h, Workspace& w, const Tables& tb, bool want_fea
     LAUNCH(ca::focal_finalize_launch(w.pc, tb.cbias, attn, rs, rs_out, B, N, w.P, mw.focus_strength, 0, nullptr, 0.5f, st));
     if (want_features) {
       // value path re-associated: sum_i a_i (A V)_i = ((a^T A) x~) Wv^T + bv   (src/model.py:204,308)
-      LAUNCH(ca::rowstats_merge_launch(w.pm, w.ps, attn, nullptr, nullptr, w.wtab, B * N, w.P, st));
+      LAUNCH(ca::rowstats_merge_launch(w.pm, w.ps, attn, nullptr, nullptr, w.wtab, B * N, N, w.P, st));
       LAUNCH(ca::colsum_e_launch(w.E, w.lde, static_cast<long long>(N) * w.lde, w.wtab, w.pc, B, N, w.P, st));
       LAUNCH(ca::focal_finalize_launch(w.pc, nullptr, w.cvec, nullptr, nullptr, B, N, w.P, 0.0f, 1, nullptr, 0.5f, st));
       LAUNCH(ca::weighted_pool_launch(w.tokens, static_cast<long long>(T) * kD, 1, w.cvec, rs, w.pool, B, N, kD, kPoolSplits, st));

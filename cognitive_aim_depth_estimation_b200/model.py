@@ -469,12 +469,12 @@ class CognitiveAimModel(nn.Module):
                 "qkv": torch.empty(B * T, 3 * _D, **bf),
                 "mlp": torch.empty(B * T, _MLP, **bf), "tokens": torch.empty(B, T, _D, **fl),
                 "xin": torch.empty(B * N, _D, **bf), "qk": torch.empty(B * N, 2 * _D, **bf),
-                "pm": torch.empty(B, N, P, **fl), "ps": torch.empty(B, N, P, **fl), "pc": torch.empty(B, P, N, **fl),
+                "pm": torch.empty(B, P, N, **fl), "ps": torch.empty(B, P, N, **fl), "pc": torch.empty(B, P, N, **fl),
                 "rmax": torch.empty(B, N, **fl), "rinv": torch.empty(B, N, **fl),
                 # span-relative exponentials of the focal scores (fp16) + the per-(row, span) factors that turn them into
                 # softmax probabilities: the column sums are a bandwidth pass over E instead of a second Q K^T
                 "E": torch.empty(B, N, 64 * ((N + 63) // 64), device=dev, dtype=torch.float16),
-                "wtab": torch.empty(B, N, P, **fl),
+                "wtab": torch.empty(B, P, N, **fl),
                 "attn": torch.empty(self.cfg.num_iterations, B, N, **fl), "cvec": torch.empty(B, N, **fl),
                 "rowscale": torch.empty(2, B, N, **fl),
                 # LayerNorm folding: per (row, 128-column span) (sum, M2) of the residual row; `h` then holds the raw rows

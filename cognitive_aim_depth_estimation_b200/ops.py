@@ -242,9 +242,11 @@ def fetch_pinned(dst, src_pinned):
 
 
 def rowstats_merge(pm, ps, weight, rmax, rinv, wtab=None):
-    rows, P = pm.numel() // pm.shape[-1], pm.shape[-1]
+    """pm, ps (and wtab): span-major [B, P, N] partials of the CA_EPI_ROWSTATS epilogue."""
+    P, n = pm.shape[-2], pm.shape[-1]
+    rows = pm.numel() // P
     e0 = _begin()
-    check(_lib.load().ca_rowstats_merge(ptr(pm), ptr(ps), ptr(weight), ptr(rmax), ptr(rinv), ptr(wtab), rows, P,
+    check(_lib.load().ca_rowstats_merge(ptr(pm), ptr(ps), ptr(weight), ptr(rmax), ptr(rinv), ptr(wtab), rows, n, P,
                                         stream_ptr()), "ca_rowstats_merge")
     _end(e0, "small", 1)
 
@@ -256,8 +258,8 @@ def colsum_e(E, wtab, pc, B, N):
     _req(wtab, torch.float32, "wtab")
     _req(pc, torch.float32, "pc")
     P = pc.shape[-2]
-    if pc.shape[-1] != N or wtab.shape[-1] != P:
-        raise ValueError("colsum_e: pc must be [B, P, N] with P = wtab.shape[-1]")
+    if pc.shape[-1] != N or wtab.shape[-2] != P or wtab.shape[-1] != N:
+        raise ValueError("colsum_e: pc and wtab must be span-major [B, P, N]")
     e0 = _begin()
     check(_lib.load().ca_colsum_e(ptr(E), E.stride(-2), E.stride(0), ptr(wtab), ptr(pc), B, N, P, stream_ptr()),
           "ca_colsum_e")

@@ -57,7 +57,7 @@ int ca_device_check(int device);            /* CA_STATUS_OK iff `device` is comp
 /* C[b] = epilogue(A[b] (M x K, lda) * W[b] (N x K, ldw)^T), bf16 operands, fp32 TMEM accumulators.
  * w_batch_stride == 0 shares W across the batch.  Unused epilogue operands may be NULL.
  * For CA_EPI_ROWSTATS/COLSUM the per-row partial buffers have P = 4*ceil(N/256) entries per row (one per 64-column
- * span of the 256-wide tiles; spans past N hold max = -inf, sum = 0). */
+ * span of the 256-wide tiles; spans past N hold max = -inf, sum = 0) and are SPAN-MAJOR: [batch, P, M]. */
 int ca_gemm_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K, int lda, int ldw, int batch,
                  long long a_batch_stride, long long w_batch_stride, int epilogue, void* out, int ldo,
                  long long out_batch_stride, const float* bias, const float* ls, const float* pos,
@@ -112,13 +112,14 @@ int ca_focal_input(const float* tokens, const float* pe, const float* rowscale, 
 int ca_fetch_pinned_f32(float* dst, const float* h_src_pinned, size_t n, void* stream);
 
 /* Focal / guidance vector stages (fp32) ---------------------------------------------------------- */
-/* Merge the per-64-column partials of CA_EPI_ROWSTATS: rmax[r] = max, rinv[r] = (weight ? weight[r] : 1) / sumexp,
- * wtab[r, s] = exp2(pm[r, s] - rmax[r]) * rinv[r]; any of the three outputs may be null (not all).
+/* Merge the per-64-column partials of CA_EPI_ROWSTATS (pm, ps: span-major [batch, P, rows_per_image]; rows = batch *
+ * rows_per_image): rmax[r] = max, rinv[r] = (weight ? weight[r] : 1) / sumexp, wtab[b, s, i] = exp2(pm[b, s, i] - rmax) * rinv
+ * (span-major like pm); any of the three outputs may be null (not all).
  * reference src/model.py:200 (row softmax statistics). */
 int ca_rowstats_merge(const float* pm, const float* ps, const float* weight, float* rmax, float* rinv, float* wtab,
-                      int rows, int P, void* stream);
+                      int rows, int rows_per_image, int P, void* stream);
 /* Column sums of the (weighted) row softmax from the span-relative exponentials E (fp16 [B, N, lde], written by
- * ca_gemm_bf16 with CA_EPI_ROWSTATS when `out` is given): pc[b, p, j] = sum_{i in row span p} E[b,i,j] * wtab[b,i,j/64]
+ * ca_gemm_bf16 with CA_EPI_ROWSTATS when `out` is given): pc[b, p, j] = sum_{i in row span p} E[b,i,j] * wtab[b,j/64,i]
  * (span-major [B, P, N]: every CTA writes one contiguous row).
  * Replaces the second Q K^T pass (CA_EPI_COLSUM) by one bandwidth-bound read of E.  src/model.py:234 (col mean), :308. */
 int ca_colsum_e(const uint16_t* E, int lde, long long e_batch_stride, const float* wtab, float* pc, int B, int N, int P,

@@ -102,23 +102,23 @@ def test_gemm_focal_stats(cuda_device, N, D):
     k = _rand((B, N, D), cuda_device, 16, 0.5).bfloat16()
     scale = 1.0 / math.sqrt(96.0)
     P = ops.stats_partials(N)
-    pm = torch.zeros((B, N, P), device=cuda_device)
-    ps = torch.zeros((B, N, P), device=cuda_device)
+    pm = torch.zeros((B, P, N), device=cuda_device)   # span-major partials
+    ps = torch.zeros((B, P, N), device=cuda_device)
     ops.gemm(q, k, ops.EPI_ROWSTATS, None, M=N, N=N, K=D, lda=D, ldw=D, batch=B, a_batch_stride=N * D,
              w_batch_stride=N * D, scale_log2=scale * ops.LOG2E, part_a=pm, part_b=ps)
     s = torch.einsum("bid,bjd->bij", q.float(), k.float()) * scale
     s2 = s * ops.LOG2E
-    rmax = pm.max(dim=-1).values
+    rmax = pm.max(dim=1).values
     assert torch.allclose(rmax, s2.max(dim=-1).values, rtol=1e-5, atol=1e-4)
-    rsum = (ps * torch.exp2(pm - rmax[..., None])).sum(-1)
+    rsum = (ps * torch.exp2(pm - rmax[:, None, :])).sum(1)
     ref_sum = torch.exp2(s2 - s2.max(dim=-1, keepdim=True).values).sum(-1)
     assert torch.allclose(rsum, ref_sum, rtol=2e-3)
     # pass B: A = keys, W = queries  ->  acc[j, i] = s[i, j]
-    pc = torch.zeros((B, N, P), device=cuda_device)
+    pc = torch.zeros((B, P, N), device=cuda_device)
     rinv = (1.0 / rsum).contiguous()
     ops.gemm(k, q, ops.EPI_COLSUM, None, M=N, N=N, K=D, lda=D, ldw=D, batch=B, a_batch_stride=N * D,
              w_batch_stride=N * D, scale_log2=scale * ops.LOG2E, part_a=pc, col_max=rmax.contiguous(), col_rinv=rinv)
-    colmean = pc.sum(-1) / N
+    colmean = pc.sum(1) / N
     ref = torch.softmax(s, dim=-1).mean(dim=1)
     assert torch.allclose(colmean, ref, rtol=5e-3, atol=1e-7), (colmean - ref).abs().max()
 
@@ -133,8 +133,8 @@ def test_focal_colsum_from_stored_exponentials(cuda_device, N, D):
     k = _rand((B, N, D), cuda_device, 22, 0.5).bfloat16()
     scale = 1.0 / math.sqrt(96.0)
     P = ops.stats_partials(N)
-    pm = torch.zeros((B, N, P), device=cuda_device)
-    ps = torch.zeros((B, N, P), device=cuda_device)
+    pm = torch.zeros((B, P, N), device=cuda_device)   # span-major partials
+    ps = torch.zeros((B, P, N), device=cuda_device)
     lde = 64 * ((N + 63) // 64)
     E = torch.full((B, N, lde), float("nan"), device=cuda_device, dtype=torch.float16)
     ops.gemm(q, k, ops.EPI_ROWSTATS, E, M=N, N=N, K=D, lda=D, ldw=D, batch=B, a_batch_stride=N * D,
@@ -143,7 +143,7 @@ def test_focal_colsum_from_stored_exponentials(cuda_device, N, D):
     s = torch.einsum("bid,bjd->bij", q.float(), k.float()) * scale
     ref = torch.softmax(s, dim=-1)
     for weight in (None, torch.rand(B, N, device=cuda_device)):
-        wtab = torch.empty((B, N, P), device=cuda_device)
+        wtab = torch.empty((B, P, N), device=cuda_device)
         pc = torch.zeros((B, P, N), device=cuda_device)   # span-major partials
         ops.rowstats_merge(pm, ps, weight, None, None, wtab)
         ops.colsum_e(E, wtab, pc, B, N)

@@ -60,7 +60,7 @@ rs = torch.rand(B, N, device=dev) + 0.5
 timed("focal_input", lambda: ops.focal_input(tokens, pe, rs, xin, B, N, D), B * N * D * 4 + pe.numel() * 4 + xin.numel() * 2)
 P = ops.stats_partials(N)
 E = (torch.rand(B, N, 64 * ((N + 63) // 64), device=dev) * 0.9 + 0.05).half()
-wtab = torch.rand(B, N, P, device=dev)
+wtab = torch.rand(B, P, N, device=dev)
 pc = torch.empty(B, P, N, device=dev)
 timed("colsum_e", lambda: ops.colsum_e(E, wtab, pc, B, N), B * N * N * 2 + wtab.numel() * 4 + pc.numel() * 4)
 heat = torch.softmax(torch.randn(B, N, device=dev), -1)
