@@ -50,7 +50,9 @@ constexpr int kAttnThreads = 6 * 32;
 constexpr int kSubBytes = kSubK * kHeadDim * 2;    // 8 KB: 64 rows x 128 B
 constexpr int kSmemK = 0;
 constexpr int kSmemV = kSmemK + kRing * kSubBytes;
-constexpr int kSmemBar = kSmemV + kRing * kSubBytes;
+constexpr int kSmemOut = kSmemV + kRing * kSubBytes;  // 4 x 2 KB: per softmax warp, 32 rows x 64 B of the output tile
+constexpr int kOutStageBytes = 32 * 64;
+constexpr int kSmemBar = kSmemOut + 4 * kOutStageBytes;
 constexpr int kAttnSmemBytes = kSmemBar + 512;
 static_assert(2 * (kAttnSmemBytes + 1024) <= 227 * 1024, "two CTAs must fit one SM");
 constexpr uint32_t kTmemCols = 256;
@@ -343,21 +345,50 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
     const uint32_t t_o = t_lane + kTmemO;
     const float scale = p.scale_log2;
     int g = 0;  // global 64-key step of this CTA
-    // Q row of an item: global -> registers (rows past the end of the image are zero)
+    // Q tile of an item: global -> registers with 4 lanes per row (8 rows x 64 contiguous bytes per load instruction; a
+    // thread-per-row load touches 32 lines per instruction), rows past the end of the image zero.  q_rows() turns the
+    // registers into the thread-per-row layout tcgen05.st wants, through the warp's 2 KB staging buffer.
+    const uint32_t stg = smem_u32(smem + kSmemOut + quad * kOutStageBytes);
+    const int orr = lane >> 2, opc = lane & 3;
     auto q_load = [&](int it, uint32_t (&qv)[32]) {
       const int bh = it / p.n_qt;
-      const int q = (it - bh * p.n_qt) * kTileQ + r;
+      const int q0 = (it - bh * p.n_qt) * kTileQ + quad * 32;
       const int b = bh / p.H;
       const int h = bh - b * p.H;
-      const bool in_range = q < p.T;
-      const uint4* src = reinterpret_cast<const uint4*>(p.qkv + (static_cast<size_t>(b) * p.T + q) * p.ld + h * kHeadDim);
+      const __nv_bfloat16* src = p.qkv + static_cast<size_t>(b) * p.T * p.ld + h * kHeadDim + opc * 8;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const uint4 w = in_range ? __ldg(src + t) : make_uint4(0u, 0u, 0u, 0u);
-        qv[4 * t + 0] = w.x;
-        qv[4 * t + 1] = w.y;
-        qv[4 * t + 2] = w.z;
-        qv[4 * t + 3] = w.w;
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = q0 + orr + 8 * i;
+          const uint4 w = row < p.T ? __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(row) * p.ld + c * 32))
+                                    : make_uint4(0u, 0u, 0u, 0u);
+          qv[16 * c + 4 * i + 0] = w.x;
+          qv[16 * c + 4 * i + 1] = w.y;
+          qv[16 * c + 4 * i + 2] = w.z;
+          qv[16 * c + 4 * i + 3] = w.w;
+        }
+      }
+    };
+    auto q_rows = [&](uint32_t (&qv)[32]) {  // in place: 4-lanes-per-row pieces -> this thread's row (64 bf16)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = orr + 8 * i;
+          sts128(stg + rr * 64 + ((opc ^ ((rr >> 1) & 3)) << 4),
+                 make_uint4(qv[16 * c + 4 * i + 0], qv[16 * c + 4 * i + 1], qv[16 * c + 4 * i + 2], qv[16 * c + 4 * i + 3]));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint4 w = lds128(stg + lane * 64 + ((t ^ ((lane >> 1) & 3)) << 4));
+          qv[16 * c + 4 * t + 0] = w.x;
+          qv[16 * c + 4 * t + 1] = w.y;
+          qv[16 * c + 4 * t + 2] = w.z;
+          qv[16 * c + 4 * t + 3] = w.w;
+        }
+        __syncwarp();
       }
     };
     // epilogue of the k-th item (global item index `it`): O / l -> bf16 -> global (token-major, head h at [64h, 64h+64))
@@ -370,24 +401,34 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
       if (warp == 2) TRACE(2, g, 0);
       tc_fence_after();
       const float inv = 1.0f / l;
-      __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * p.T + q) * p.ldo + h * kHeadDim;
+      // TMEM hands every thread one output ROW; written straight from there each 16-byte store of a warp touches 32
+      // different lines (8 such instructions per item and warp).  Each 32-column half goes through the warp's 2 KB
+      // staging buffer instead (16-byte pieces XOR-swizzled with bits 1-2 of the row: both sides conflict-free) and
+      // leaves with 4 lanes per row: 8 rows x 64 contiguous bytes per store instruction.
+      const int q0 = q - lane;  // first row of this warp
+      __nv_bfloat16* obase = p.out + static_cast<size_t>(b) * p.T * p.ldo + h * kHeadDim + opc * 8;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t o[32];
         tmem_ld32(t_o + c * 32, o);
         tmem_ld_wait();
-        if (q < p.T) {
-          uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(o[8 * t + 0]) * inv, __uint_as_float(o[8 * t + 1]) * inv);
-            w.y = pack_bf16x2(__uint_as_float(o[8 * t + 2]) * inv, __uint_as_float(o[8 * t + 3]) * inv);
-            w.z = pack_bf16x2(__uint_as_float(o[8 * t + 4]) * inv, __uint_as_float(o[8 * t + 5]) * inv);
-            w.w = pack_bf16x2(__uint_as_float(o[8 * t + 6]) * inv, __uint_as_float(o[8 * t + 7]) * inv);
-            o4[t] = w;
-          }
+        for (int t = 0; t < 4; ++t) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * t + 0]) * inv, __uint_as_float(o[8 * t + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * t + 2]) * inv, __uint_as_float(o[8 * t + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * t + 4]) * inv, __uint_as_float(o[8 * t + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * t + 6]) * inv, __uint_as_float(o[8 * t + 7]) * inv);
+          sts128(stg + lane * 64 + ((t ^ ((lane >> 1) & 3)) << 4), w);
         }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = orr + 8 * i;
+          const uint4 w = lds128(stg + rr * 64 + ((opc ^ ((rr >> 1) & 3)) << 4));
+          if (q0 + rr < p.T) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(q0 + rr) * p.ldo + c * 32) = w;
+        }
+        __syncwarp();
       }
     };
     if (p.stagger > 0 && blockIdx.x >= gridDim.x / 2) {  // de-phase the two CTAs of an SM
@@ -398,6 +439,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
     if (it_cur >= 0) {  // Q of the first item
       uint32_t qv[32];
       q_load(it_cur, qv);
+      q_rows(qv);
       tmem_st32(t_lane + kTmemQ, qv);
       tmem_st_wait();
       tc_fence_before();
@@ -537,6 +579,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
         if (k > 0) epilogue(k - 1, it_prev, l_prev);
         if (warp == 2) TRACE(2, g, 1);
         if (it_next >= 0) {  // Q of the next item (its buffer was last read by item k-1, which is complete)
+          q_rows(qv);
           tmem_st32(t_lane + kTmemQ + ((k + 1) & 1) * 32, qv);
           tmem_st_wait();
           if (warp == 2) TRACE(2, g, 2);
