@@ -561,10 +561,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnArgs
         step_sum = exponentials(v, pk);
 #else
         step_sum = exponentials(v, pk);
+        // Stale reference?  A P >= 2 out of the MUFU (up to +inf, or NaN) makes the row sum >= 2 — sums of a valid step are
+        // below 64 * 2^-64 — so ONE compare covers the MUFU elements; the polynomial elements can also wrap into a
+        // negative or denormal pattern for inputs beyond their range, so their packed words (8 of the 32 at the shipped
+        // 25 % share) are still OR-ed and tested for the sign / exponent-MSB bits.
         uint32_t any = 0;
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) any |= pk[c] | pk[c + 1];
-        if (__any_sync(0xffffffffu, (any & 0xC000C000u) != 0u)) {  // some P >= 2, negative or NaN: the reference is stale
+        for (int t = 0; t < kSubK / 8; ++t) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            if (w >= 4 - static_cast<int>((kPolyMask >> (2 * t)) & 3u)) any |= pk[4 * t + w];
+        }
+        if (__any_sync(0xffffffffu, (any & 0xC000C000u) != 0u || !(step_sum < 2.0f))) {  // the reference is stale
           load_row();
           exact_reference(v, false, bb);
           step_sum = exponentials(v, pk);
